@@ -1,0 +1,430 @@
+// K1: persistent, warp-specialised bf16 GEMM for sm_100a.
+//   warp 0      : TMA producer (one elected lane) -- A/B tiles -> 128B-swizzled smem ring
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane) -- tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
+//   warps 2..5  : epilogue -- tcgen05.ld TMEM -> registers -> fused epilogue -> vectorised global stores
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue; 2 accumulator stages so
+// the epilogue of tile i overlaps the main loop of tile i+1), and a static persistent tile schedule.
+//
+// Replaces the reference's tf.layers.dense / tf.matmul call sites listed in include/merlot_b200.h (K1).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BUDGET = 196608;  // operand ring; + 1024 alignment slack + barriers
+
+struct GemmDev {
+  int M, N, K;
+  int splits, kb_per_split, num_kb;
+  int m_blocks, n_blocks;
+  void* out; int ld_out;
+  void* out2; int ld_out2;
+  const float* bias;
+  const bf16* resid; int ld_resid;
+  const bf16* aux; int ld_aux;
+  float alpha;
+  uint32_t flags;
+  uint32_t drop_thresh16; float drop_scale; uint64_t seed; uint32_t site;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512: power of two)
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Epilogue for 8 consecutive columns [col, col+8) of one row. v[] holds alpha-unscaled accumulators.
+__device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, float (&v)[8]) {
+  const bool full = (col + 8 <= p.N);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+  if (p.bias != nullptr) {
+    if (full) {
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+    }
+  }
+  if (p.flags & MERLOT_GEMM_GELU) {
+    if (p.out2 != nullptr) {  // keep the pre-activation for the backward pass
+      bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col;
+      if (full) {
+        uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(o) = pk;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) o[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.flags & MERLOT_GEMM_MUL_DGELU) {
+    const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
+    if (full) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(a));
+      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      v[0] *= gelu_erf_grad(f0.x); v[1] *= gelu_erf_grad(f0.y); v[2] *= gelu_erf_grad(f1.x); v[3] *= gelu_erf_grad(f1.y);
+      v[4] *= gelu_erf_grad(f2.x); v[5] *= gelu_erf_grad(f2.y); v[6] *= gelu_erf_grad(f3.x); v[7] *= gelu_erf_grad(f3.y);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+    }
+  }
+  if (p.flags & MERLOT_GEMM_DROPOUT) {
+    uint64_t lin = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;  // col % 8 == 0, N % 8 == 0 enforced on host
+    uint32_t keep = dropout_keep8(p.seed, p.site, lin >> 3, p.drop_thresh16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.0f;
+  }
+  if (p.resid != nullptr) {
+    const bf16* r = p.resid + (size_t)row * p.ld_resid + col;
+    if (full) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(r));
+      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y; v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] += __bfloat162float(r[i]);
+    }
+  }
+  // ---- store ----
+  const bool second = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
+  if (p.flags & MERLOT_GEMM_OUT_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ld_out + col;
+    if (p.flags & MERLOT_GEMM_ATOMIC) {
+      if (full) {
+        red_add_v4(o, v[0], v[1], v[2], v[3]);
+        red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) atomicAdd(o + i, v[i]);
+      }
+    } else {
+      if (full && ((p.ld_out & 3) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) o[i] = v[i];
+      }
+    }
+  } else {
+    bf16* o = second ? reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ld_out2 + col
+                     : reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col;
+    if (full) {
+      uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(o) = pk;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) o[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % p.splits;
+        const int mn = tile / p.splits;
+        const int n_blk = mn % p.n_blocks;
+        const int m_blk = mn / p.n_blocks;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(sa + c * (BLOCK_K * 128), &tma_a, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (BLOCK_K * 128), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = A_MN ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
+            const uint64_t db = B_MN ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int lane_base = (warp & 3) * 32;  // TMEM lane window this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mn = tile / p.splits;
+      const int n_blk = mn % p.n_blocks;
+      const int m_blk = mn / p.n_blocks;
+      const int row = m_blk * BLOCK_M + lane_base + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)lane_base << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < p.M && col0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              epilogue8(p, row, col, v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+                            cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, p);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(g != nullptr, MERLOT_EINVAL, "gemm: null descriptor");
+  MB_REQUIRE(g->a && g->b && g->out, MERLOT_EINVAL, "gemm: null operand pointer");
+  MB_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, MERLOT_ESHAPE, "gemm: non-positive dims M=%d N=%d K=%d", g->M, g->N,
+             g->K);
+  MB_REQUIRE((g->lda % 8) == 0 && (g->ldb % 8) == 0, MERLOT_ESHAPE,
+             "gemm: lda/ldb must be multiples of 8 bf16 elements for TMA (lda=%d ldb=%d)", g->lda, g->ldb);
+  MB_REQUIRE(((uintptr_t)g->a % 16) == 0 && ((uintptr_t)g->b % 16) == 0, MERLOT_ESHAPE,
+             "gemm: operand base pointers must be 16-byte aligned");
+  MB_REQUIRE(g->lda >= (g->a_mn_major ? g->M : g->K) && g->ldb >= (g->b_mn_major ? g->N : g->K), MERLOT_ESHAPE,
+             "gemm: leading dimension smaller than the row length");
+  const bool out_f32 = g->flags & MERLOT_GEMM_OUT_F32;
+  MB_REQUIRE(!(g->flags & MERLOT_GEMM_ATOMIC) || out_f32, MERLOT_EINVAL, "gemm: ATOMIC requires OUT_F32");
+  MB_REQUIRE(!(g->flags & MERLOT_GEMM_MUL_DGELU) || g->aux, MERLOT_EINVAL, "gemm: MUL_DGELU requires aux");
+  MB_REQUIRE(g->ld_out >= g->N, MERLOT_ESHAPE, "gemm: ld_out < N");
+  if (!out_f32)
+    MB_REQUIRE((g->ld_out % 8) == 0 && ((uintptr_t)g->out % 16) == 0, MERLOT_ESHAPE,
+               "gemm: bf16 output needs ld_out %% 8 == 0 and a 16-byte aligned base");
+  if (g->resid) MB_REQUIRE((g->ld_resid % 8) == 0, MERLOT_ESHAPE, "gemm: ld_resid %% 8 != 0");
+  if (g->aux) MB_REQUIRE((g->ld_aux % 8) == 0, MERLOT_ESHAPE, "gemm: ld_aux %% 8 != 0");
+  if (g->out2) MB_REQUIRE((g->ld_out2 % 8) == 0, MERLOT_ESHAPE, "gemm: ld_out2 %% 8 != 0");
+  if (g->flags & MERLOT_GEMM_DROPOUT)
+    MB_REQUIRE((g->N % 8) == 0 && g->dropout_p >= 0.f && g->dropout_p < 1.f, MERLOT_ESHAPE,
+               "gemm: dropout needs N %% 8 == 0 and 0 <= p < 1");
+
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.out = g->out; p.ld_out = g->ld_out; p.out2 = g->out2; p.ld_out2 = g->ld_out2;
+  p.bias = g->bias;
+  p.resid = reinterpret_cast<const bf16*>(g->resid); p.ld_resid = g->ld_resid;
+  p.aux = reinterpret_cast<const bf16*>(g->aux); p.ld_aux = g->ld_aux;
+  p.alpha = g->alpha;
+  p.flags = g->flags;
+  if ((g->flags & MERLOT_GEMM_DROPOUT) && g->dropout_p > 0.f) {
+    p.drop_thresh16 = (uint32_t)(g->dropout_p * 65536.0f + 0.5f);
+    p.drop_scale = 1.0f / (1.0f - g->dropout_p);
+    p.seed = g->dropout_seed;
+    p.site = g->dropout_site;
+  } else {
+    p.flags &= ~MERLOT_GEMM_DROPOUT;
+  }
+
+  const int sms = num_sms();
+  p.m_blocks = ceil_div(g->M, BLOCK_M);
+  p.num_kb = ceil_div(g->K, BLOCK_K);
+  // ---- tile width: minimise wave-quantisation loss; BN=256 halves per-FLOP smem traffic so it wins ties ----
+  int bn = g->block_n;
+  if (bn == 0) {
+    double best = -1;
+    for (int cand : {256, 128}) {
+      long long tiles = (long long)p.m_blocks * ceil_div(g->N, cand);
+      long long waves = ceil_div_ll(tiles, sms);
+      double useful = (double)g->N / (double)(ceil_div(g->N, cand) * cand);
+      double eff = (double)tiles / (double)(waves * sms) * useful * (cand == 256 ? 1.0 : 0.93);
+      if (eff > best + 1e-9) { best = eff; bn = cand; }
+    }
+  }
+  MB_REQUIRE(bn == 128 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128 or 256 (got %d)", bn);
+  p.n_blocks = ceil_div(g->N, bn);
+  // ---- split-K (wgrad): fill the machine when the MN tile count is small ----
+  int splits = g->splits;
+  const int mn_tiles = p.m_blocks * p.n_blocks;
+  if (splits <= 0) {
+    splits = 1;
+    if ((g->flags & MERLOT_GEMM_ATOMIC) && mn_tiles < sms) {
+      splits = sms / mn_tiles;
+      int max_by_k = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;  // keep >= 4 k-blocks per split
+      if (splits > max_by_k) splits = max_by_k;
+      if (splits < 1) splits = 1;
+    }
+  }
+  MB_REQUIRE(splits == 1 || (g->flags & MERLOT_GEMM_ATOMIC), MERLOT_EINVAL, "gemm: splits>1 requires ATOMIC");
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  p.splits = ceil_div(p.num_kb, p.kb_per_split);  // no empty splits
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (g->a_mn_major)
+    rc = make_tmap_bf16_2d(&ta, g->a, (uint64_t)g->M, (uint64_t)g->K, (uint64_t)g->lda, 64, BLOCK_K);
+  else
+    rc = make_tmap_bf16_2d(&ta, g->a, (uint64_t)g->K, (uint64_t)g->M, (uint64_t)g->lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  if (g->b_mn_major)
+    rc = make_tmap_bf16_2d(&tb, g->b, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->ldb, 64, BLOCK_K);
+  else
+    rc = make_tmap_bf16_2d(&tb, g->b, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BLOCK_K, (uint32_t)bn);
+  if (rc) return rc;
+
+  const long long tiles = (long long)mn_tiles * p.splits;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+
+#define MB_GEMM_DISPATCH(BN_)                                                                   \
+  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true>(ta, tb, p, grid, stream);   \
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true>(ta, tb, p, grid, stream); \
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false>(ta, tb, p, grid, stream); \
+  return launch_gemm_inst<BN_, true, false>(ta, tb, p, grid, stream);
+  if (bn == 256) { MB_GEMM_DISPATCH(256) }
+  MB_GEMM_DISPATCH(128)
+#undef MB_GEMM_DISPATCH
+}
