@@ -80,6 +80,97 @@ typedef struct merlot_gemm {
 
 int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K2/K3/K4: masked softmax attention, FlashAttention-tiled on tcgen05 (probabilities never materialised in HBM).
+ * Replaces utils/transformer.py:98-127 (scores = q k^T / sqrt(d); scores*m - 1e10*(1-m); softmax; probs @ v), its
+ * tf.gradients, and the column sums of `self_attn_probs` consumed by model/modeling.py:428 (mask_inputs).
+ *  qkv   : bf16 [B*S, ld_qkv], columns [0,H)=q, [H,2H)=k, [2H,3H)=v with head h at column h*64 (the fused QKV GEMM out).
+ *  valid : uint8 [B*S] token validity (input_id != 0, model/modeling.py:148,363) or NULL = all valid (ViT, :239 of
+ *          utils/vision_transformer.py).  mask[q,k] = valid[q] & valid[k] (model/modeling.py:158).
+ *  lse   : f32 [B, heads, S] log-sum-exp of the masked scaled scores (written by fwd, read by bwd / colsum).
+ *  fwd   : ctx bf16 [B*S, ld_ctx] <- softmax(.) v
+ *  bwd   : needs ctx, d_ctx (bf16 [B*S, ld_ctx]); writes dsum (scratch f32 [B,heads,S]), accumulates dq in dq_accum
+ *          (f32 [B*S, ld_dq], MUST be zero on entry; it is re-zeroed on exit) and writes dqkv bf16 [B*S, ld_dqkv].
+ *  colsum: colsum[b,k] += (1/heads) * sum_q P[b,h,q,k]   (f32 [B,S]; caller zeroes it once per stack).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct merlot_attn {
+  int B, S, heads, head_dim;
+  const void* qkv; int ld_qkv;
+  const void* valid;
+  float scale;                 /* 1/sqrt(head_dim), utils/transformer.py:99-100 */
+  void* ctx; int ld_ctx;
+  float* lse;
+  const void* d_ctx;
+  float* dsum;
+  float* dq_accum; int ld_dq;
+  void* dqkv; int ld_dqkv;
+  float* colsum;
+} merlot_attn_t;
+
+int merlot_attention_fwd(const merlot_attn_t* a, void* stream);
+int merlot_attention_bwd(const merlot_attn_t* a, void* stream);
+int merlot_attention_colsum(const merlot_attn_t* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5: LayerNorm (utils/model_utils.py:113-130): fp32 statistics over the last dim, biased variance, eps inside rsqrt,
+ *     y = x*s - mean*s + beta with s = rsqrt(var+eps)*gamma.  One warp per row, 128-bit accesses.  H % 8 == 0, H <= 1024.
+ *     Optional fused inverted dropout on y (utils/model_utils.py:335-349; used after `embed_norm`, modeling.py:293-294).
+ *     Row remap (map_per > 0): logical row r is written to / read from row (r / map_per) * map_stride + map_off + r % map_per,
+ *     which places the viz and lang pieces side by side in the joint sequence (the tf.concat at model/modeling.py:151).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct merlot_ln {
+  const void* x; int x_f32; int ld_x;
+  void* y; int y_f32; int ld_y;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd;          /* optional saved statistics [rows] */
+  long long rows; int H; float eps;
+  int map_per, map_stride, map_off;  /* output row remap; map_per = 0 disables */
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+} merlot_ln_t;
+int merlot_layernorm_fwd(const merlot_ln_t* d, void* stream);
+
+/* dx = LN'(dy) (+ dres); dgamma += sum dy*xhat; dbeta += sum dy.  dy is read through the same row remap / dropout mask. */
+typedef struct merlot_ln_bwd {
+  const void* dy; int dy_f32; int ld_dy;
+  const void* x; int x_f32; int ld_x;
+  const float* mean; const float* rstd; const float* gamma;
+  const void* dres; int ld_dres;     /* optional residual-stream gradient added to dx (same dtype as dx) */
+  void* dx; int dx_f32; int ld_dx;
+  float* dgamma; float* dbeta;       /* accumulated (+=) */
+  void* workspace;                   /* merlot_layernorm_bwd_workspace_bytes(H) */
+  long long rows; int H;
+  int map_per, map_stride, map_off;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+} merlot_ln_bwd_t;
+size_t merlot_layernorm_bwd_workspace_bytes(int H);
+int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream);
+
+/* bias gradient of a tf.layers.dense: out[n] += sum_m dy[m,n], optionally through the forward dropout mask */
+int merlot_bias_grad(const void* dy, int dy_f32, int ld, long long rows, int N, float* out, float dropout_p,
+                     uint64_t seed, uint32_t site, void* stream);
+/* backward of utils/model_utils.py:335-349 dropout with the counter-based mask the forward epilogue used */
+int merlot_dropout_apply(const void* x_bf16, int ld_x, void* y_bf16, int ld_y, long long rows, int N, float p, uint64_t seed,
+                         uint32_t site, void* stream);
+/* one_hot_gather (utils/model_utils.py:225-235) as a real gather, and its transpose (scatter-add) */
+int merlot_gather_rows(const void* src, int src_f32, int ld_s, const int* idx, void* dst, int dst_f32, int ld_d, int n, int H,
+                       void* stream);
+int merlot_scatter_add_rows(const void* src, int src_f32, int ld_s, const int* idx, void* dst, int dst_f32, int ld_d, int n,
+                            int H, float scale, void* stream);
+/* erf-GeLU (utils/model_utils.py:96-110) and its derivative on small fp32 head tensors */
+int merlot_gelu_f32(const float* x, float* y, long long n, void* stream);
+int merlot_gelu_bwd_f32(const float* dy, const float* pre, float* dx, long long n, void* stream);
+/* bfloat16_getter cast (utils/model_utils.py:572-602) */
+int merlot_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+int merlot_cast_bf16_to_f32(const void* x, float* y, long long n, void* stream);
+/* tf.math.l2_normalize(axis=-1) (model/modeling.py:43) */
+int merlot_l2norm_fwd(const float* x, float* y, float* inv, int rows, int H, void* stream);
+int merlot_l2norm_bwd(const float* dy, const float* y, const float* inv, float* dx, int rows, int H, void* stream);
+/* raw_cross_entropy_with_logits (utils/model_utils.py:313-332) + argmax accuracy; bwd: dlogits = coeff[r]*(softmax-onehot) */
+int merlot_softmax_ce_fwd(const float* logits, int ld, const int* labels, int rows, int C, float* loss, float* lse,
+                          float* correct, void* stream);
+int merlot_softmax_ce_bwd(const float* logits, int ld, const int* labels, int rows, int C, const float* lse,
+                          const float* coeff, void* dlogits, int dlogits_f32, int ld_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,3 +90,19 @@ def exported_symbols_from_header() -> list[str]:
     hdr = (_HERE.parent / "include" / "merlot_b200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(merlot_[a-z0-9_]+)\s*\(", hdr)))
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("S", C.c_int), ("heads", C.c_int), ("head_dim", C.c_int),
+        ("qkv", C.c_void_p), ("ld_qkv", C.c_int),
+        ("valid", C.c_void_p),
+        ("scale", C.c_float),
+        ("ctx", C.c_void_p), ("ld_ctx", C.c_int),
+        ("lse", C.c_void_p),
+        ("d_ctx", C.c_void_p),
+        ("dsum", C.c_void_p),
+        ("dq_accum", C.c_void_p), ("ld_dq", C.c_int),
+        ("dqkv", C.c_void_p), ("ld_dqkv", C.c_int),
+        ("colsum", C.c_void_p),
+    ]

@@ -1,0 +1,630 @@
+// K2/K3/K4: masked softmax attention on tcgen05 tensor cores, FlashAttention-style (probabilities never hit HBM).
+//
+// Replaces utils/transformer.py:98-127 (scores = q k^T / sqrt(d); scores*m - 1e10*(1-m); softmax; probs @ v) and its
+// tf.gradients, plus the consumers of the materialised probabilities: the head-mean column sums that
+// model/modeling.py:428 (mask_inputs) takes from `self_attn_probs` (utils/transformer.py:208-209,238).
+//
+// Layout: q/k/v are read in place from the fused QKV GEMM output [tokens, 3H] (columns [0,H) = q, [H,2H) = k,
+// [2H,3H) = v, head h at column h*64) through one 2-D TMA map; ctx / d_ctx are [tokens, H].  Head size is 64.
+//
+// Mask semantics (reference :109-112): m[q,k] = valid[q] & valid[k].  A masked entry's score is
+// exactly -1e10; a padding QUERY row therefore has all scores equal and softmaxes to uniform 1/S over all S keys.
+// We realise that row as all-zero scores (identical softmax, but keeps log-sum-exp = log S representable).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+constexpr int AT_M = 128;   // query rows per tile (TMEM lanes)
+constexpr int AT_N = 128;   // keys per tile
+constexpr int AT_D = 64;    // head size
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnDev {
+  int B, S, heads, H;
+  const uint8_t* valid;  // [B*S] or null (all valid)
+  float scale;
+  bf16* ctx; int ld_ctx;         // fwd out [B*S, H]
+  float* lse;                    // [B, heads, S] natural-log LSE of the masked, scaled scores
+  // backward
+  float* dsum;                   // [B, heads, S]  D = rowsum(dO * O)
+  float* dq_accum; int ld_dq;    // fp32 [B*S, H], atomically accumulated
+  bf16* dqkv; int ld_dqkv;       // bf16 [B*S, 3H]; this kernel writes the K and V column blocks
+  // K4
+  float* colsum;                 // [B, S] += sum_q mean_h P[b,h,q,k]
+};
+
+// score in the log2 domain: sc2 = scale * log2(e)
+__device__ __forceinline__ float masked_score(float s, float sc2, bool vq, bool vk, bool in_range) {
+  if (!in_range) return -INFINITY;
+  if (!vq) return 0.0f;           // padding query row: uniform softmax (see header comment)
+  return vk ? s * sc2 : -1e10f * LOG2E;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// forward
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int FWD_SMEM = 16384 * 3 + 32768 + 1024 + 128;
+
+__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = smem + 49152;  // [128 q rows][128 keys] bf16, two 64-key K-major atoms of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 32768);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S, H = p.H;
+  const int tok0 = b * S;
+  const int n_kv = (S + AT_N - 1) / AT_N;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 16384);
+    tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
+    mbar_arrive_expect_tx(bar_k, 16384);
+    tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0);
+    mbar_arrive_expect_tx(bar_v, 16384);
+    tma_load_2d(sV, &tm_qkv, bar_v, 2 * H + h * AT_D, tok0);
+  }
+
+  const int q = q0 + tid;
+  const bool q_in = q < S;
+  const bool vq = q_in ? (p.valid ? p.valid[tok0 + q] != 0 : true) : true;
+  float m_run = -INFINITY, l_run = 0.f;
+  float o[AT_D];
+#pragma unroll
+  for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
+  const float sc2 = p.scale * LOG2E;
+
+  for (int j = 0; j < n_kv; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph);
+      tc_fence_after();
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {  // K tile is free once S = Q K^T has completed
+      mbar_arrive_expect_tx(bar_k, 16384);
+      tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + (j + 1) * AT_N);
+    }
+    const int k0 = j * AT_N;
+    // ---- pass A: row max of the masked, scaled scores (log2 domain) ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < AT_N / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tS + lane_off + c * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int kk = k0 + c * 32 + i;
+        const bool in = kk < S;
+        const bool vk = in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
+        float x = masked_score(__uint_as_float(r[i]), sc2, vq, vk, in);
+        mx = fmaxf(mx, x);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
+    float rowsum = 0.f;
+    // ---- pass B: p = 2^(x - m), write P (bf16) into the K-major swizzled A tile ----
+#pragma unroll 1
+    for (int c = 0; c < AT_N / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tS + lane_off + c * 32, r);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float pv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int kk = k0 + c * 32 + i + u;
+          const bool in = kk < S;
+          const bool vk = in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
+          float x = masked_score(__uint_as_float(r[i + u]), sc2, vq, vk, in);
+            pv[u] = exp2f(x - m_new);
+          rowsum += pv[u];
+        }
+        pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+      }
+      uint8_t* atom = sP + (c >> 1) * 16384;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t chunk = (uint32_t)((c & 1) * 4 + g);
+        *reinterpret_cast<uint4*>(atom + sw128_offset(tid, chunk)) =
+            make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+      }
+    }
+    l_run = l_run * alpha + rowsum;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph);
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < AT_N / 16; ++k) {
+        const uint64_t da = desc_kmajor(pa + (k >> 2) * 16384, k & 3);
+        const uint64_t db = desc_mnmajor(va, k, 0);  // single 64-wide chunk: LBO unused
+        umma_bf16_ss(tO, da, db, idesc_o, k > 0);
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {  // V tile is free once O_j = P V has completed
+      mbar_arrive_expect_tx(bar_v, 16384);
+      tma_load_2d(sV, &tm_qkv, bar_v, 2 * H + h * AT_D, tok0 + (j + 1) * AT_N);
+    }
+#pragma unroll
+    for (int c = 0; c < AT_D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tO + lane_off + c * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+  }
+
+  if (q_in) {
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.ctx + (size_t)(tok0 + q) * p.ld_ctx + h * AT_D;
+#pragma unroll
+    for (int g = 0; g < AT_D / 8; ++g) {
+      uint4 pk = make_uint4(pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv), pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv),
+                            pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv), pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv));
+      *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+    }
+    if (p.lse) p.lse[((size_t)b * p.heads + h) * S + q] = (m_run + log2f(l_run)) * LN2;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// backward: one CTA per (key tile, head, batch); loops over query tiles.
+//   S^T = K Q^T, dP^T = V dO^T (keys on TMEM lanes) -> P^T, dS^T in smem -> dV += P^T dO, dK += dS^T Q, dQ_i = dS K
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int BWD_SMEM = 16384 * 4 + 32768 * 2 + 1024 + 1024 + 128;
+
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + 16384;
+  uint8_t* sQ = smem + 32768;
+  uint8_t* sdO = smem + 49152;
+  uint8_t* sPT = smem + 65536;        // P^T  [128 keys][128 q] bf16, two 64-col atoms
+  uint8_t* sdST = smem + 65536 + 32768;  // dS^T same layout
+  float* s_lse = reinterpret_cast<float*>(smem + 65536 + 65536);
+  float* s_dsum = s_lse + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 65536 + 1024);
+  uint64_t *bar_kv = bars, *bar_q = bars + 1, *bar_1 = bars + 2, *bar_2 = bars + 3;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S, H = p.H;
+  const int tok0 = b * S;
+  const int n_q = (S + AT_M - 1) / AT_M;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_1, 1); mbar_init(bar_2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 32768);
+    tma_load_2d(sK, &tm_qkv, bar_kv, H + h * AT_D, tok0 + k0);
+    tma_load_2d(sV, &tm_qkv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
+  }
+  const int kk = k0 + tid;  // this thread's key row
+  const bool k_in = kk < S;
+  const bool vk = k_in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
+
+  constexpr uint32_t idesc_st = make_idesc_bf16(AT_N, AT_M, 0, 0);   // S^T, dP^T : both operands K-major (d)
+  constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
+  constexpr uint32_t idesc_dq = make_idesc_bf16(AT_M, AT_D, 1, 1);   // A = dS (MN-major view of dS^T), B = K MN-major
+  const float sc2 = p.scale * LOG2E;
+
+  for (int i = 0; i < n_q; ++i) {
+    const uint32_t ph = i & 1;
+    const int q0 = i * AT_M;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, 32768);
+      tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
+      tma_load_2d(sdO, &tm_do, bar_q, h * AT_D, tok0 + q0);
+    }
+    {  // stage lse / D for this query tile
+      const int q = q0 + tid;
+      const size_t o = ((size_t)b * p.heads + h) * S + q;
+      s_lse[tid] = (q < S) ? p.lse[o] * LOG2E : 0.f;
+      s_dsum[tid] = (q < S) ? p.dsum[o] : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQ), da = smem_u32(sdO);
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
+      umma_commit(bar_1);
+    }
+    mbar_wait(bar_1, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < AT_M / 32; ++c) {
+      uint32_t rs[32], rd[32];
+      tmem_ld_32x32(tST + lane_off + c * 32, rs);
+      tmem_ld_32x32(tdPT + lane_off + c * 32, rd);
+      tmem_wait_ld();
+      uint32_t pk[16], dk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ql = c * 32 + e + u;
+          const int q = q0 + ql;
+          const bool q_in = q < S;
+          const bool vq = q_in ? (p.valid ? p.valid[tok0 + q] != 0 : true) : true;
+          float x = masked_score(__uint_as_float(rs[e + u]), sc2, vq, vk, k_in);
+          float pr = (q_in && k_in) ? exp2f(x - s_lse[ql]) : 0.f;
+          pv[u] = pr;
+          dv[u] = pr * (__uint_as_float(rd[e + u]) - s_dsum[ql]) * p.scale;
+        }
+        pk[e >> 1] = pack_bf16x2(pv[0], pv[1]);
+        dk[e >> 1] = pack_bf16x2(dv[0], dv[1]);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t off = (uint32_t)(c >> 1) * 16384 + sw128_offset(tid, (uint32_t)((c & 1) * 4 + g));
+        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQ), da = smem_u32(sdO), ka = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < AT_M / 16; ++k)  // dV += P^T dO   (contraction over q)
+        umma_bf16_ss(tdV, desc_kmajor(pa + (k >> 2) * 16384, k & 3), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
+#pragma unroll
+      for (int k = 0; k < AT_M / 16; ++k)  // dK += dS^T Q
+        umma_bf16_ss(tdK, desc_kmajor(sa + (k >> 2) * 16384, k & 3), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
+#pragma unroll
+      for (int k = 0; k < AT_N / 16; ++k)  // dQ_i = dS K      (contraction over keys; A = MN-major view of dS^T)
+        umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 16384), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);
+      umma_commit(bar_2);
+    }
+    mbar_wait(bar_2, ph);
+    tc_fence_after();
+    {  // dQ partial: lanes are query rows here
+      const int q = q0 + tid;
+#pragma unroll
+      for (int c = 0; c < AT_D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tdQ + lane_off + c * 32, r);
+        tmem_wait_ld();
+        if (q < S) {
+          float* dst = p.dq_accum + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                         : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // sQ/sdO/s_lse reuse + TMEM S^T/dP^T/dQ reuse by the next iteration
+  }
+  // ---- dK, dV for this key tile (exclusive rows) ----
+  tc_fence_after();
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t t = which == 0 ? tdK : tdV;
+#pragma unroll
+    for (int c = 0; c < AT_D / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(t + lane_off + c * 32, r);
+      tmem_wait_ld();
+      if (k_in) {
+        bf16* dst = p.dqkv + (size_t)(tok0 + kk) * p.ld_dqkv + (which == 0 ? H : 2 * H) + h * AT_D + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// D[b,h,q] = sum_d dO[q,hd] * O[q,hd]   (one warp per (token, head) pair would waste lanes; 8 lanes x 8 elems per head)
+__global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, int ld, float* __restrict__ dsum,
+                                 int B, int S, int heads) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long item = gid >> 3;  // (token, head)
+  const int sub = (int)(gid & 7);
+  const long long total = (long long)B * S * heads;
+  float acc = 0.f;
+  if (item < total) {
+    const int hh = (int)(item % heads);
+    const long long tok = item / heads;
+    const size_t off = (size_t)tok * ld + hh * AT_D + sub * 8;
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(o + off));
+    uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + off));
+    const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* pg = reinterpret_cast<const uint32_t*>(&g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 x = unpack_bf16x2(pa[i]), y = unpack_bf16x2(pg[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (item < total && sub == 0) {
+    const int hh = (int)(item % heads);
+    const long long tok = item / heads;
+    const int bb = (int)(tok / S), q = (int)(tok % S);
+    dsum[((size_t)bb * heads + hh) * S + q] = acc;
+  }
+}
+
+// dq fp32 accumulator -> bf16 q-block of dqkv, and re-zero the accumulator for the next layer
+__global__ void attn_dq_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv, long long rows,
+                                      int H) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = H / 8;
+  if (gid >= rows * per_row) return;
+  const long long r = gid / per_row;
+  const int c = (int)(gid % per_row) * 8;
+  float4* src = reinterpret_cast<float4*>(dq + (size_t)r * ld_dq + c);
+  float4 a = src[0], b = src[1];
+  *reinterpret_cast<uint4*>(dqkv + (size_t)r * ld_dqkv + c) =
+      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+  src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// K4: colsum[b,k] += (1/heads) * sum_q P[b,h,q,k], recomputed from (q,k,lse); keys on TMEM lanes so the reduction over
+// queries runs along registers.  One CTA per (key tile, head, batch).
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int CS_SMEM = 16384 * 2 + 1024 + 512 + 128;
+
+__global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sQ = smem + 16384;
+  float* s_lse = reinterpret_cast<float*>(smem + 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 512);
+  uint64_t *bar_k = bars, *bar_q = bars + 1, *bar_s = bars + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S, H = p.H, tok0 = b * S;
+  const int n_q = (S + AT_M - 1) / AT_M;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(bar_k, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_k, 16384);
+    tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + k0);
+  }
+  const int kk = k0 + tid;
+  const bool k_in = kk < S;
+  const bool vk = k_in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
+  constexpr uint32_t idesc = make_idesc_bf16(AT_N, AT_M, 0, 0);
+  const float sc2 = p.scale * LOG2E;
+  float acc = 0.f;
+  for (int i = 0; i < n_q; ++i) {
+    const uint32_t ph = i & 1;
+    const int q0 = i * AT_M;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
+    }
+    {
+      const int q = q0 + tid;
+      s_lse[tid] = (q < S) ? p.lse[((size_t)b * p.heads + h) * S + q] * LOG2E : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (i == 0) mbar_wait(bar_k, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+      const uint32_t ka = smem_u32(sK), qa = smem_u32(sQ);
+#pragma unroll
+      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc, k > 0);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < AT_M / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem + lane_off + c * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int ql = c * 32 + e, q = q0 + ql;
+        if (q < S && k_in) {
+          const bool vq = p.valid ? p.valid[tok0 + q] != 0 : true;
+          float x = masked_score(__uint_as_float(r[e]), sc2, vq, vk, true);
+          acc += exp2f(x - s_lse[ql]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (k_in) atomicAdd(p.colsum + (size_t)b * S + kk, acc / (float)p.heads);
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+static int check_common(const merlot_attn_t* a) {
+  MB_REQUIRE(a != nullptr, MERLOT_EINVAL, "attention: null descriptor");
+  MB_REQUIRE(a->B > 0 && a->S > 0 && a->heads > 0, MERLOT_ESHAPE, "attention: bad dims B=%d S=%d heads=%d", a->B, a->S,
+             a->heads);
+  MB_REQUIRE(a->head_dim == 64, MERLOT_ESHAPE, "attention: head size must be 64 (got %d)", a->head_dim);
+  MB_REQUIRE(a->qkv != nullptr && a->ld_qkv >= 3 * a->heads * 64 && (a->ld_qkv % 8) == 0, MERLOT_ESHAPE,
+             "attention: qkv must be [tokens, >=3H] with ld %% 8 == 0");
+  return MERLOT_OK;
+}
+
+static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
+  memset(p, 0, sizeof(*p));
+  p->B = a->B; p->S = a->S; p->heads = a->heads; p->H = a->heads * 64;
+  p->valid = reinterpret_cast<const uint8_t*>(a->valid);
+  p->scale = a->scale;
+  p->ctx = reinterpret_cast<bf16*>(a->ctx); p->ld_ctx = a->ld_ctx;
+  p->lse = a->lse;
+  p->dsum = a->dsum;
+  p->dq_accum = a->dq_accum; p->ld_dq = a->ld_dq;
+  p->dqkv = reinterpret_cast<bf16*>(a->dqkv); p->ld_dqkv = a->ld_dqkv;
+  p->colsum = a->colsum;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_common(a);
+  if (rc) return rc;
+  MB_REQUIRE(a->ctx != nullptr && (a->ld_ctx % 8) == 0, MERLOT_EINVAL, "attention_fwd: ctx missing or ld_ctx %% 8 != 0");
+  AttnDev p; fill_dev(a, &p);
+  CUtensorMap tm;
+  rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, 128);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+  dim3 grid(ceil_div(a->S, AT_M), a->heads, a->B);
+  attn_fwd_kernel<<<grid, 128, FWD_SMEM, stream>>>(tm, p);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_common(a);
+  if (rc) return rc;
+  MB_REQUIRE(a->ctx && a->d_ctx && a->lse && a->dsum && a->dq_accum && a->dqkv, MERLOT_EINVAL,
+             "attention_bwd: ctx, d_ctx, lse, dsum, dq_accum and dqkv are all required");
+  MB_REQUIRE((a->ld_ctx % 8) == 0 && (a->ld_dqkv % 8) == 0 && (a->ld_dq % 4) == 0, MERLOT_ESHAPE,
+             "attention_bwd: leading dimensions must keep 16-byte alignment");
+  AttnDev p; fill_dev(a, &p);
+  const int H = p.H;
+  const long long tokens = (long long)a->B * a->S;
+  {  // D = rowsum(dO * O)
+    const long long threads = tokens * a->heads * 8;
+    attn_dsum_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(a->ctx), reinterpret_cast<const bf16*>(a->d_ctx), a->ld_ctx,
+        a->dsum, a->B, a->S, a->heads);
+    MB_CHECK_LAUNCH();
+  }
+  CUtensorMap tm, tdo;
+  rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)tokens, (uint64_t)a->ld_qkv, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tdo, a->d_ctx, (uint64_t)a->ld_ctx, (uint64_t)tokens, (uint64_t)a->ld_ctx, 64, 128);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)); attr = true; }
+  dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
+  attn_bwd_kernel<<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
+  MB_CHECK_LAUNCH();
+  {
+    const long long n = tokens * (H / 8);
+    attn_dq_finish_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(a->dq_accum, a->ld_dq, p.dqkv, a->ld_dqkv,
+                                                                              tokens, H);
+    MB_CHECK_LAUNCH();
+  }
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_attention_colsum(const merlot_attn_t* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = check_common(a);
+  if (rc) return rc;
+  MB_REQUIRE(a->lse && a->colsum, MERLOT_EINVAL, "attention_colsum: lse and colsum are required");
+  AttnDev p; fill_dev(a, &p);
+  CUtensorMap tm;
+  rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, 128);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM)); attr = true; }
+  dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
+  attn_colsum_kernel<<<grid, 128, CS_SMEM, stream>>>(tm, p);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}

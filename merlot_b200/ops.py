@@ -84,3 +84,59 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     g.splits, g.block_n = splits, block_n
     L.check(L.lib().merlot_gemm_bf16(C.byref(g), _stream()))
     return out
+
+
+def _attn_desc(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[torch.Tensor]) -> L.AttnDesc:
+    _require_cuda(qkv, valid)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * S
+    a = L.AttnDesc()
+    a.B, a.S, a.heads, a.head_dim = B, S, heads, qkv.shape[1] // (3 * heads)
+    a.qkv, a.ld_qkv = qkv.data_ptr(), qkv.stride(0)
+    if valid is not None:
+        assert valid.dtype == torch.uint8 and valid.numel() == B * S and valid.is_contiguous()
+        a.valid = valid.data_ptr()
+    a.scale = 1.0 / (a.head_dim ** 0.5)
+    return a
+
+
+def attention_fwd(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[torch.Tensor] = None,
+                  ctx: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
+    """K2: ctx[B*S,H] = softmax(mask(q k^T / sqrt(d))) v, reading q/k/v in place from the fused qkv buffer."""
+    a = _attn_desc(qkv, B, S, heads, valid)
+    H = heads * a.head_dim
+    if ctx is None:
+        ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device)
+    if lse is None:
+        lse = torch.empty((B, heads, S), dtype=torch.float32, device=qkv.device)
+    a.ctx, a.ld_ctx, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
+    L.check(L.lib().merlot_attention_fwd(C.byref(a), _stream()))
+    return ctx, lse
+
+
+def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_accum=None, dsum=None):
+    """K3: dqkv[B*S,3H] from d_ctx.  dq_accum must be zero on entry (it is returned zeroed)."""
+    a = _attn_desc(qkv, B, S, heads, valid)
+    H = heads * a.head_dim
+    dev = qkv.device
+    if dqkv is None:
+        dqkv = torch.empty((B * S, 3 * H), dtype=torch.bfloat16, device=dev)
+    if dq_accum is None:
+        dq_accum = torch.zeros((B * S, H), dtype=torch.float32, device=dev)
+    if dsum is None:
+        dsum = torch.empty((B, heads, S), dtype=torch.float32, device=dev)
+    a.ctx, a.ld_ctx, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
+    assert d_ctx.stride(0) == ctx.stride(0)
+    a.d_ctx, a.dsum = d_ctx.data_ptr(), dsum.data_ptr()
+    a.dq_accum, a.ld_dq = dq_accum.data_ptr(), dq_accum.stride(0)
+    a.dqkv, a.ld_dqkv = dqkv.data_ptr(), dqkv.stride(0)
+    L.check(L.lib().merlot_attention_bwd(C.byref(a), _stream()))
+    return dqkv
+
+
+def attention_colsum(qkv, lse, colsum, B, S, heads, valid=None):
+    """K4: colsum[B,S] += mean_h sum_q P[b,h,q,k] (recomputed from q,k,lse)."""
+    a = _attn_desc(qkv, B, S, heads, valid)
+    assert colsum.dtype == torch.float32 and colsum.numel() == B * S
+    a.lse, a.colsum = lse.data_ptr(), colsum.data_ptr()
+    L.check(L.lib().merlot_attention_colsum(C.byref(a), _stream()))
+    return colsum
