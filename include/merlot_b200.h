@@ -171,6 +171,113 @@ int merlot_softmax_ce_fwd(const float* logits, int ld, const int* labels, int ro
 int merlot_softmax_ce_bwd(const float* logits, int ld, const int* labels, int rows, int C, const float* lse,
                           const float* coeff, void* dlogits, int dlogits_f32, int ld_d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Transformer stack driver (utils/transformer.py:171-247 `transformer`, pre-LN; forward and explicit backward).
+ * One call enqueues a whole 12-layer stack.  Used three times per pretraining step: ViT (vision_transformer.py:247),
+ * language-only (modeling.py:370) and joint (modeling.py:173) -- the last two with the SAME layer_params (scope
+ * `encoder`, AUTO_REUSE), whose gradients therefore accumulate.
+ * Weights: bf16 copies in the reference's [in,out] layout (w_qkv is [H,3H] = query|key|value kernels side by side).
+ * Gradients: fp32, accumulated (+=) into g_*; zero them once per step.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct merlot_layer_params {
+  const float *ln1_gamma, *ln1_beta;      /* LayerNorm_attn_ln0 */
+  const void* w_qkv; const float* b_qkv;  /* query_layer|key_layer|value_layer fused: [H,3H], [3H] */
+  const void* w_o;   const float* b_o;    /* context_projection_layer [H,H] */
+  const float *ln2_gamma, *ln2_beta;      /* LayerNorm_mlp_ln0 */
+  const void* w_1;   const float* b_1;    /* intermediate [H,I] */
+  const void* w_2;   const float* b_2;    /* output [I,H] */
+  float *g_ln1_gamma, *g_ln1_beta, *g_w_qkv, *g_b_qkv, *g_w_o, *g_b_o, *g_ln2_gamma, *g_ln2_beta, *g_w_1, *g_b_1, *g_w_2, *g_b_2;
+} merlot_layer_params_t;
+
+typedef struct merlot_stack {
+  int B, S, H, I, heads, layers;
+  const merlot_layer_params_t* layer_params;   /* HOST array [layers] of device pointers */
+  const float *final_gamma, *final_beta;       /* LayerNorm_ln_final */
+  float *d_final_gamma, *d_final_beta;
+  const void* valid;                           /* uint8 [B*S] or NULL */
+  const void* h_in;                            /* bf16 [B*S, H] stack input */
+  void* y;                                     /* bf16 [B*S, H] = LN_final(h_last) */
+  void* act_arena;                             /* merlot_stack_activation_bytes() */
+  int save_for_backward;                       /* 0: forward only (arena holds one layer) */
+  float hidden_dropout_p; float attention_dropout_p; uint64_t dropout_seed; uint32_t dropout_site_base;
+  float* attn_colsum;                          /* optional f32 [B,S]: += sum over layers,queries of head-mean probs */
+  /* backward */
+  const void* dy;                              /* bf16 [B*S, H] gradient wrt y */
+  void* dh_in;                                 /* bf16 [B*S, H] gradient wrt h_in (optional) */
+  void* scratch;                               /* merlot_stack_scratch_bytes() */
+} merlot_stack_t;
+
+size_t merlot_stack_activation_bytes(const merlot_stack_t* s);
+size_t merlot_stack_scratch_bytes(const merlot_stack_t* s);
+int merlot_stack_forward(const merlot_stack_t* s, void* stream);
+int merlot_stack_backward(const merlot_stack_t* s, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K6/K7: token assembly around the stacks (see csrc/assemble.cu for the reference lines each one replaces).
+ * ------------------------------------------------------------------------------------------------------------ */
+int merlot_patch_im2col(const void* image_bf16_nhwc, void* a_bf16, int N, int H0, int W0, int P, void* stream);
+int merlot_vit_assemble_fwd(const float* patch, const float* pos_table, const float* cls_emb, float* xsum, int N, int h1,
+                            int w1, int ncls, int tab_w, int H, void* stream);
+int merlot_vit_assemble_bwd(const float* dxsum, void* dpatch_bf16, int N, int np, int ncls, int H, void* stream);
+int merlot_viz_assemble_fwd(const void* hv_bf16, const float* img_idx_pe, const int* img_idx, const float* final_pos,
+                            const float* final_cls, float* xsum, float* img_trg, int N, int h1, int w1, int ncls, int sp,
+                            int tab_w, int H, void* stream);
+int merlot_viz_assemble_bwd(const float* dxsum, const float* d_img_trg, void* dhv_bf16, int N, int h1, int w1, int ncls,
+                            int sp, int H, void* stream);
+int merlot_embed_fwd(const int* ids, const float* emb, const float* pos, float* xsum, long long R, int L, int H, void* stream);
+int merlot_group_rowsum(const float* src, int ld, int groups, int per, int t0, int nt, const int* idxmap, float* dst,
+                        int ld_dst, int H, void* stream);
+int merlot_segment_rowsum_scatter(const float* src, int ld, int n_seg, int per, const int* idx, float* dst, int ld_dst, int H,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K12: MerlotModel.mask_inputs (model/modeling.py:381-489) with the random draws injected by the caller
+ * (gumbel = -log(-log(U)) of utils/model_utils.py:647; two SpanBERT categorical draws; the 10/80/10 option draw;
+ * uniform replacement ids in [100, vocab)).  Bit-exact integer outputs.
+ *  w_non = 0.01f, w_delta = float(topk_val - 0.01), logw_* = log of the two weights, w_max = reduce_max(mask_weight).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct merlot_mask {
+  const int* ids; const float* attn_summ; const float* gumbel; const int* span_lower; const int* span_upper;
+  const int* option; const int* rand_ids;
+  int* masked_ids; int* masked_idx; void* valid_out;
+  int B, L, num_topk, num_to_mask, do_spanbert, mask_token;
+  float w_delta, w_non, logw_top, logw_non, w_max;
+} merlot_mask_t;
+int merlot_mask_inputs(const merlot_mask_t* m, void* stream);
+int merlot_ids_valid(const int* ids, void* valid_u8, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K10: fused AdamW on a contiguous slice of the flat parameter arena (utils/optimization.py:339-416, :267-288).
+ * lr_t = lr * schedule * sqrt(1-beta2^t)/(1-beta1^t) is computed by the host (optimization.py:352-358).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct merlot_adamw {
+  float* p; float* g; void* m; void* v;   /* fp32 master, fp32 grad, bf16 m, packed bf16 v */
+  void* p_bf16;                           /* optional bf16 compute copy of p */
+  long long n;
+  float beta1, one_minus_beta1, beta2, one_minus_beta2, epsilon, lr_t, weight_decay, grad_scale;
+  int zero_grad;
+} merlot_adamw_t;
+int merlot_adamw_step(const merlot_adamw_t* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss-head glue (model/modeling.py:491-668): integer index/label construction and weighted reductions, on device.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* is_valid of the joint sequence: viz part all true (modeling.py:106-107), lang part ids != 0 (:148) */
+int merlot_joint_valid(const int* ids, void* valid_u8, int B, int P, int L, void* stream);
+/* rows of the masked positions in the joint sequence and their targets (modeling.py:533-536) */
+int merlot_mlm_index(const int* ids, const int* masked_idx, int* rows, int* targets, int B, int L, int k, int P, void* stream);
+/* allpairs_temporal_labels (modeling.py:598-620) + the 0.01/1.0 pair weights (:635,649-650) */
+int merlot_temporal_labels(const int* video_src_ids, const int* shuffled_idx_img, int* labels, float* weights, int B, int n,
+                           void* stream);
+/* out2[0] = sum(l*w)/denom, out2[1] = sum(correct*w)/(sum w + 1e-5); coeff[r] = scale*w[r]/denom.
+ * denom_mode 0: denom = R (reduce_mean); 1: denom = sum w + 1e-5 (modeling.py:543).  w: weights, or labels != 0, or 1. */
+int merlot_weighted_loss(const float* per_row_loss, const float* correct, const float* weights, const int* nz_labels, int R,
+                         int denom_mode, float scale, float* out2, float* coeff, void* stream);
+/* tiny strided fp32 matmul C = alpha * A B^T + beta * C for the contrastive logits (modeling.py:521) and their grads */
+int merlot_small_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, float* C,
+                          int ldc, int M, int N, int K, float alpha, float beta, void* stream);
+int merlot_axpby_f32(const float* x, float* y, long long n, float a, float b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

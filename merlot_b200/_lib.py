@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
     l.merlot_abi_version.restype = C.c_int
     l.merlot_launch_count.restype = C.c_longlong
     l.merlot_reset_launch_count.restype = None
+    for fn in ("merlot_stack_activation_bytes", "merlot_stack_scratch_bytes", "merlot_layernorm_bwd_workspace_bytes"):
+        getattr(l, fn).restype = C.c_size_t
     _lib = l
     return l
 
@@ -105,4 +107,79 @@ class AttnDesc(C.Structure):
         ("dq_accum", C.c_void_p), ("ld_dq", C.c_int),
         ("dqkv", C.c_void_p), ("ld_dqkv", C.c_int),
         ("colsum", C.c_void_p),
+    ]
+
+
+class LnDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_f32", C.c_int), ("ld_x", C.c_int),
+        ("y", C.c_void_p), ("y_f32", C.c_int), ("ld_y", C.c_int),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("rows", C.c_longlong), ("H", C.c_int), ("eps", C.c_float),
+        ("map_per", C.c_int), ("map_stride", C.c_int), ("map_off", C.c_int),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
+    ]
+
+
+class LnBwdDesc(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_f32", C.c_int), ("ld_dy", C.c_int),
+        ("x", C.c_void_p), ("x_f32", C.c_int), ("ld_x", C.c_int),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p),
+        ("dres", C.c_void_p), ("ld_dres", C.c_int),
+        ("dx", C.c_void_p), ("dx_f32", C.c_int), ("ld_dx", C.c_int),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("rows", C.c_longlong), ("H", C.c_int),
+        ("map_per", C.c_int), ("map_stride", C.c_int), ("map_off", C.c_int),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32),
+    ]
+
+
+class LayerParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_gamma", "ln1_beta", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_gamma", "ln2_beta", "w_1", "b_1", "w_2", "b_2",
+        "g_ln1_gamma", "g_ln1_beta", "g_w_qkv", "g_b_qkv", "g_w_o", "g_b_o", "g_ln2_gamma", "g_ln2_beta", "g_w_1", "g_b_1",
+        "g_w_2", "g_b_2")]
+
+
+class StackDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("S", C.c_int), ("H", C.c_int), ("I", C.c_int), ("heads", C.c_int), ("layers", C.c_int),
+        ("layer_params", C.POINTER(LayerParams)),
+        ("final_gamma", C.c_void_p), ("final_beta", C.c_void_p),
+        ("d_final_gamma", C.c_void_p), ("d_final_beta", C.c_void_p),
+        ("valid", C.c_void_p),
+        ("h_in", C.c_void_p),
+        ("y", C.c_void_p),
+        ("act_arena", C.c_void_p),
+        ("save_for_backward", C.c_int),
+        ("hidden_dropout_p", C.c_float), ("attention_dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("dropout_site_base", C.c_uint32),
+        ("attn_colsum", C.c_void_p),
+        ("dy", C.c_void_p),
+        ("dh_in", C.c_void_p),
+        ("scratch", C.c_void_p),
+    ]
+
+
+class MaskDesc(C.Structure):
+    _fields_ = [
+        ("ids", C.c_void_p), ("attn_summ", C.c_void_p), ("gumbel", C.c_void_p), ("span_lower", C.c_void_p),
+        ("span_upper", C.c_void_p), ("option", C.c_void_p), ("rand_ids", C.c_void_p),
+        ("masked_ids", C.c_void_p), ("masked_idx", C.c_void_p), ("valid_out", C.c_void_p),
+        ("B", C.c_int), ("L", C.c_int), ("num_topk", C.c_int), ("num_to_mask", C.c_int), ("do_spanbert", C.c_int),
+        ("mask_token", C.c_int),
+        ("w_delta", C.c_float), ("w_non", C.c_float), ("logw_top", C.c_float), ("logw_non", C.c_float), ("w_max", C.c_float),
+    ]
+
+
+class AdamDesc(C.Structure):
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_bf16", C.c_void_p),
+        ("n", C.c_longlong),
+        ("beta1", C.c_float), ("one_minus_beta1", C.c_float), ("beta2", C.c_float), ("one_minus_beta2", C.c_float),
+        ("epsilon", C.c_float), ("lr_t", C.c_float), ("weight_decay", C.c_float), ("grad_scale", C.c_float),
+        ("zero_grad", C.c_int),
     ]

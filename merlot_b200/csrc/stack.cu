@@ -1,0 +1,276 @@
+// Native driver of one pre-LN transformer stack (utils/transformer.py:171-247): forward and hand-written backward,
+// enqueuing the K1/K2/K3/K5 kernels of this library on one stream.  The reference builds this loop in Python/TF and lets
+// tf.gradients derive the backward graph (utils/optimization.py:176); here both directions are explicit.
+//
+// Per layer (residual stream h is bf16, statistics fp32):
+//   x1 = LN(h); qkv = x1 Wqkv + b; ctx = attn(qkv); hmid = h + drop(ctx Wo + bo);
+//   x2 = LN(hmid); pre = x2 W1 + b1; act = gelu(pre); hout = hmid + drop(act W2 + b2)
+// and y = LN_final(h_last).  Weights are bf16 copies in the reference's [in,out] layout: the forward GEMM reads them as
+// an MN-major B operand, dgrad reads the same buffer as a K-major B operand, wgrad reads both activations MN-major and
+// red.adds fp32 into the flat gradient arena (so the shared `encoder` weights accumulate both of their passes).
+#include "host_common.h"
+
+namespace mb {
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct LayerAct {
+  char *x1, *qkv, *ctx, *hmid, *x2, *pre, *act, *hout;
+  float *lse, *mean1, *rstd1, *mean2, *rstd2;
+};
+
+static size_t layer_act_bytes(const merlot_stack_t* s) {
+  const size_t M = (size_t)s->B * s->S, H = s->H, I = s->I;
+  return align_up(M * H * 2) * 5 + align_up(M * 3 * H * 2) + align_up(M * I * 2) * 2 +
+         align_up((size_t)s->B * s->heads * s->S * 4) + align_up(M * 4) * 4;
+}
+
+static LayerAct carve(const merlot_stack_t* s, char* base) {
+  const size_t M = (size_t)s->B * s->S, H = s->H, I = s->I;
+  LayerAct a;
+  char* p = base;
+  auto take = [&](size_t n) { char* r = p; p += align_up(n); return r; };
+  a.x1 = take(M * H * 2); a.qkv = take(M * 3 * H * 2); a.ctx = take(M * H * 2); a.hmid = take(M * H * 2);
+  a.x2 = take(M * H * 2); a.pre = take(M * I * 2); a.act = take(M * I * 2); a.hout = take(M * H * 2);
+  a.lse = (float*)take((size_t)s->B * s->heads * s->S * 4);
+  a.mean1 = (float*)take(M * 4); a.rstd1 = (float*)take(M * 4); a.mean2 = (float*)take(M * 4); a.rstd2 = (float*)take(M * 4);
+  return a;
+}
+
+static int check_stack(const merlot_stack_t* s) {
+  MB_REQUIRE(s != nullptr, MERLOT_EINVAL, "stack: null descriptor");
+  MB_REQUIRE(s->B > 0 && s->S > 0 && s->layers > 0, MERLOT_ESHAPE, "stack: bad dims B=%d S=%d layers=%d", s->B, s->S, s->layers);
+  MB_REQUIRE(s->H == s->heads * 64, MERLOT_ESHAPE,
+             "stack: hidden_size %d != num_attention_heads %d * 64 (utils/transformer.py:16-19 raises ValueError on the same mismatch)",
+             s->H, s->heads);
+  MB_REQUIRE(s->H % 8 == 0 && s->I % 8 == 0 && s->H <= 1024, MERLOT_ESHAPE, "stack: H, I must be multiples of 8 and H <= 1024");
+  MB_REQUIRE(s->layer_params && s->h_in && s->act_arena && s->final_gamma && s->final_beta, MERLOT_EINVAL, "stack: null pointer");
+  MB_REQUIRE(s->attention_dropout_p == 0.f, MERLOT_ENOTIMPL,
+             "stack: attention_probs_dropout_prob > 0 is not provided (0.0 in every shipped config; utils/transformer.py:114-115)");
+  return MERLOT_OK;
+}
+
+static int ln_fwd(const void* x, void* y, const float* g, const float* b, float* mean, float* rstd, long long rows, int H,
+                  cudaStream_t st) {
+  merlot_ln_t d;
+  memset(&d, 0, sizeof(d));
+  d.x = x; d.ld_x = H; d.y = y; d.ld_y = H; d.gamma = g; d.beta = b; d.mean = mean; d.rstd = rstd; d.rows = rows; d.H = H;
+  d.eps = 1e-5f;
+  return merlot_layernorm_fwd(&d, st);
+}
+
+static int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres,
+                  void* dx, float* dgamma, float* dbeta, void* ws, long long rows, int H, cudaStream_t st) {
+  merlot_ln_bwd_t d;
+  memset(&d, 0, sizeof(d));
+  d.dy = dy; d.ld_dy = H; d.x = x; d.ld_x = H; d.mean = mean; d.rstd = rstd; d.gamma = gamma; d.dres = dres; d.ld_dres = H;
+  d.dx = dx; d.ld_dx = H; d.dgamma = dgamma; d.dbeta = dbeta; d.workspace = ws; d.rows = rows; d.H = H;
+  return merlot_layernorm_bwd(&d, st);
+}
+
+static merlot_gemm_t gemm_base(int M, int N, int K) {
+  merlot_gemm_t g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.alpha = 1.f;
+  return g;
+}
+
+// y[M,N] = x[M,K] @ W[K,N] + bias (+ epilogue)
+static int linear_fwd(const void* x, int K, const void* W, int N, const float* bias, int M, merlot_gemm_t extra, cudaStream_t st) {
+  merlot_gemm_t g = extra;
+  g.M = M; g.N = N; g.K = K;
+  g.a = x; g.lda = K; g.a_mn_major = 0;
+  g.b = W; g.ldb = N; g.b_mn_major = 1;
+  g.bias = bias;
+  return merlot_gemm_bf16(&g, st);
+}
+// dW[K,N] += x[M,K]^T @ dy[M,N]
+static int linear_wgrad(const void* x, int K, const void* dy, int N, float* dW, int M, cudaStream_t st) {
+  merlot_gemm_t g = gemm_base(K, N, M);
+  g.a = x; g.lda = K; g.a_mn_major = 1;
+  g.b = dy; g.ldb = N; g.b_mn_major = 1;
+  g.out = dW; g.ld_out = N;
+  g.flags = MERLOT_GEMM_OUT_F32 | MERLOT_GEMM_ATOMIC;
+  return merlot_gemm_bf16(&g, st);
+}
+// dx[M,K] = dy[M,N] @ W[K,N]^T (+ epilogue)
+static int linear_dgrad(const void* dy, int N, const void* W, int K, void* dx, int M, merlot_gemm_t extra, cudaStream_t st) {
+  merlot_gemm_t g = extra;
+  g.M = M; g.N = K; g.K = N;
+  g.a = dy; g.lda = N; g.a_mn_major = 0;
+  g.b = W; g.ldb = N; g.b_mn_major = 0;
+  g.out = dx; g.ld_out = K;
+  return merlot_gemm_bf16(&g, st);
+}
+
+#define RC(expr)            \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" size_t merlot_stack_activation_bytes(const merlot_stack_t* s) {
+  if (!s) return 0;
+  const size_t M = (size_t)s->B * s->S;
+  const size_t per = layer_act_bytes(s);
+  return per * (s->save_for_backward ? (size_t)s->layers : 1) + align_up(M * 4) * 2;
+}
+
+extern "C" size_t merlot_stack_scratch_bytes(const merlot_stack_t* s) {
+  if (!s) return 0;
+  const size_t M = (size_t)s->B * s->S, H = s->H, I = s->I;
+  return align_up(M * H * 2) * 4 + align_up(M * 3 * H * 2) + align_up(M * I * 2) + align_up(M * H * 4) +
+         align_up((size_t)s->B * s->heads * s->S * 4) + align_up(merlot_layernorm_bwd_workspace_bytes(s->H));
+}
+
+extern "C" int merlot_stack_forward(const merlot_stack_t* s, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  RC(check_stack(s));
+  MB_REQUIRE(s->y != nullptr, MERLOT_EINVAL, "stack_forward: y is null");
+  const int M = s->B * s->S, H = s->H, I = s->I;
+  const size_t per = layer_act_bytes(s);
+  char* arena = reinterpret_cast<char*>(s->act_arena);
+  const size_t nlay_saved = s->save_for_backward ? (size_t)s->layers : 1;
+  float* mean_f = reinterpret_cast<float*>(arena + per * nlay_saved);
+  float* rstd_f = reinterpret_cast<float*>(arena + per * nlay_saved + align_up((size_t)M * 4));
+  const void* h = s->h_in;
+  for (int l = 0; l < s->layers; ++l) {
+    const merlot_layer_params_t& P = s->layer_params[l];
+    LayerAct A = carve(s, arena + (s->save_for_backward ? per * l : 0));
+    // forward-only mode ping-pongs the residual stream between hmid/hout of the single saved layer: h (= previous hout)
+    // is consumed by the out-proj epilogue before hout is rewritten by FFN2, so the aliasing is safe.
+    RC(ln_fwd(h, A.x1, P.ln1_gamma, P.ln1_beta, A.mean1, A.rstd1, M, H, st));
+    {
+      merlot_gemm_t e = gemm_base(0, 0, 0);
+      e.out = A.qkv; e.ld_out = 3 * H;
+      RC(linear_fwd(A.x1, H, P.w_qkv, 3 * H, P.b_qkv, M, e, st));
+    }
+    {
+      merlot_attn_t a;
+      memset(&a, 0, sizeof(a));
+      a.B = s->B; a.S = s->S; a.heads = s->heads; a.head_dim = 64; a.qkv = A.qkv; a.ld_qkv = 3 * H; a.valid = s->valid;
+      a.scale = 0.125f; a.ctx = A.ctx; a.ld_ctx = H; a.lse = A.lse;
+      RC(merlot_attention_fwd(&a, st));
+      if (s->attn_colsum) {
+        a.colsum = s->attn_colsum;
+        RC(merlot_attention_colsum(&a, st));
+      }
+    }
+    {
+      merlot_gemm_t e = gemm_base(0, 0, 0);
+      e.out = A.hmid; e.ld_out = H; e.resid = h; e.ld_resid = H;
+      if (s->hidden_dropout_p > 0.f) {
+        e.flags |= MERLOT_GEMM_DROPOUT; e.dropout_p = s->hidden_dropout_p; e.dropout_seed = s->dropout_seed;
+        e.dropout_site = s->dropout_site_base + 2 * l;
+      }
+      RC(linear_fwd(A.ctx, H, P.w_o, H, P.b_o, M, e, st));
+    }
+    RC(ln_fwd(A.hmid, A.x2, P.ln2_gamma, P.ln2_beta, A.mean2, A.rstd2, M, H, st));
+    {
+      merlot_gemm_t e = gemm_base(0, 0, 0);
+      e.out = A.pre; e.ld_out = I; e.out2 = A.act; e.ld_out2 = I; e.flags = MERLOT_GEMM_GELU;
+      RC(linear_fwd(A.x2, H, P.w_1, I, P.b_1, M, e, st));
+    }
+    {
+      merlot_gemm_t e = gemm_base(0, 0, 0);
+      e.out = A.hout; e.ld_out = H; e.resid = A.hmid; e.ld_resid = H;
+      if (s->hidden_dropout_p > 0.f) {
+        e.flags |= MERLOT_GEMM_DROPOUT; e.dropout_p = s->hidden_dropout_p; e.dropout_seed = s->dropout_seed;
+        e.dropout_site = s->dropout_site_base + 2 * l + 1;
+      }
+      RC(linear_fwd(A.act, I, P.w_2, H, P.b_2, M, e, st));
+    }
+    h = A.hout;
+  }
+  RC(ln_fwd(h, s->y, s->final_gamma, s->final_beta, mean_f, rstd_f, M, H, st));
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  RC(check_stack(s));
+  MB_REQUIRE(s->save_for_backward, MERLOT_EINVAL, "stack_backward: forward was not run with save_for_backward");
+  MB_REQUIRE(s->dy && s->scratch && s->d_final_gamma && s->d_final_beta, MERLOT_EINVAL, "stack_backward: null pointer");
+  const int M = s->B * s->S, H = s->H, I = s->I;
+  const size_t per = layer_act_bytes(s);
+  char* arena = reinterpret_cast<char*>(s->act_arena);
+  float* mean_f = reinterpret_cast<float*>(arena + per * s->layers);
+  float* rstd_f = reinterpret_cast<float*>(arena + per * s->layers + align_up((size_t)M * 4));
+  // scratch carve-up
+  char* p = reinterpret_cast<char*>(s->scratch);
+  auto take = [&](size_t n) { char* r = p; p += align_up(n); return r; };
+  char* dhA = take((size_t)M * H * 2);
+  char* dhB = take((size_t)M * H * 2);
+  char* dtmp = take((size_t)M * H * 2);   // dx of a sub-block / d_ctx
+  char* dmask = take((size_t)M * H * 2);  // dropout-masked copy of the stream gradient
+  char* dqkv = take((size_t)M * 3 * H * 2);
+  char* dpre = take((size_t)M * I * 2);
+  float* dq_acc = (float*)take((size_t)M * H * 4);
+  float* dsum = (float*)take((size_t)s->B * s->heads * s->S * 4);
+  void* lnws = take(merlot_layernorm_bwd_workspace_bytes(H));
+  MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)M * H * 4, st));
+
+  const bool drop = s->hidden_dropout_p > 0.f;
+  char* dh = dhA;
+  char* dh_other = dhB;
+  {  // final LN
+    LayerAct A = carve(s, arena + per * (s->layers - 1));
+    RC(ln_bwd(s->dy, A.hout, mean_f, rstd_f, s->final_gamma, nullptr, dh, s->d_final_gamma, s->d_final_beta, lnws, M, H, st));
+  }
+  for (int l = s->layers - 1; l >= 0; --l) {
+    const merlot_layer_params_t& P = s->layer_params[l];
+    LayerAct A = carve(s, arena + per * l);
+    const void* h_in = (l == 0) ? s->h_in : (const void*)carve(s, arena + per * (l - 1)).hout;
+    // ---- FFN2: hout = hmid + drop(act W2 + b2) ----
+    const void* d = dh;
+    if (drop) {
+      RC(merlot_dropout_apply(dh, H, dmask, H, M, H, s->hidden_dropout_p, s->dropout_seed, s->dropout_site_base + 2 * l + 1, st));
+      d = dmask;
+    }
+    RC(merlot_bias_grad(d, 0, H, M, H, P.g_b_2, 0.f, 0, 0, st));
+    RC(linear_wgrad(A.act, I, d, H, P.g_w_2, M, st));
+    {
+      merlot_gemm_t e = gemm_base(0, 0, 0);
+      e.flags = MERLOT_GEMM_MUL_DGELU; e.aux = A.pre; e.ld_aux = I;
+      RC(linear_dgrad(d, H, P.w_2, I, dpre, M, e, st));
+    }
+    // ---- FFN1 ----
+    RC(merlot_bias_grad(dpre, 0, I, M, I, P.g_b_1, 0.f, 0, 0, st));
+    RC(linear_wgrad(A.x2, H, dpre, I, P.g_w_1, M, st));
+    RC(linear_dgrad(dpre, I, P.w_1, H, dtmp, M, gemm_base(0, 0, 0), st));
+    // ---- LN2: d_hmid = dh + LN'(dx2) ----
+    RC(ln_bwd(dtmp, A.hmid, A.mean2, A.rstd2, P.ln2_gamma, dh, dh_other, P.g_ln2_gamma, P.g_ln2_beta, lnws, M, H, st));
+    { char* t = dh; dh = dh_other; dh_other = t; }
+    // ---- attention output projection: hmid = h + drop(ctx Wo + bo) ----
+    d = dh;
+    if (drop) {
+      RC(merlot_dropout_apply(dh, H, dmask, H, M, H, s->hidden_dropout_p, s->dropout_seed, s->dropout_site_base + 2 * l, st));
+      d = dmask;
+    }
+    RC(merlot_bias_grad(d, 0, H, M, H, P.g_b_o, 0.f, 0, 0, st));
+    RC(linear_wgrad(A.ctx, H, d, H, P.g_w_o, M, st));
+    RC(linear_dgrad(d, H, P.w_o, H, dtmp, M, gemm_base(0, 0, 0), st));  // d_ctx
+    // ---- attention ----
+    {
+      merlot_attn_t a;
+      memset(&a, 0, sizeof(a));
+      a.B = s->B; a.S = s->S; a.heads = s->heads; a.head_dim = 64; a.qkv = A.qkv; a.ld_qkv = 3 * H; a.valid = s->valid;
+      a.scale = 0.125f; a.ctx = A.ctx; a.ld_ctx = H; a.lse = A.lse; a.d_ctx = dtmp; a.dsum = dsum; a.dq_accum = dq_acc;
+      a.ld_dq = H; a.dqkv = dqkv; a.ld_dqkv = 3 * H;
+      RC(merlot_attention_bwd(&a, st));
+    }
+    // ---- QKV projection ----
+    RC(merlot_bias_grad(dqkv, 0, 3 * H, M, 3 * H, P.g_b_qkv, 0.f, 0, 0, st));
+    RC(linear_wgrad(A.x1, H, dqkv, 3 * H, P.g_w_qkv, M, st));
+    RC(linear_dgrad(dqkv, 3 * H, P.w_qkv, H, dtmp, M, gemm_base(0, 0, 0), st));
+    // ---- LN1: d_h_in = d_hmid + LN'(dx1) ----
+    void* dst = (l == 0 && s->dh_in) ? s->dh_in : (void*)dh_other;
+    RC(ln_bwd(dtmp, h_in, A.mean1, A.rstd1, P.ln1_gamma, dh, dst, P.g_ln1_gamma, P.g_ln1_beta, lnws, M, H, st));
+    { char* t = dh; dh = dh_other; dh_other = t; }
+  }
+  return MERLOT_OK;
+}
