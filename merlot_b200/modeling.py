@@ -1,0 +1,812 @@
+"""Host-side mirror of the reference's `MerlotModel` (model/modeling.py:47-668) over the sm_100a C-ABI.
+
+Same constructor arguments, attributes and methods as the reference class, so `model_fn`-style callers
+(model/modeling.py:691-713, downstream/sort_story/get_zero_shot_logits.py:58-79) read the same.  Construction *is* the
+forward pass (the reference builds the TF graph there).  Differences forced by leaving TF1:
+  * variables live in a `ParamStore` passed as `params=` (the reference keeps them in the TF graph);
+  * random draws that the reference takes from tf.random.* are injectable (`mask_draws=`, `dropout_seed=`);
+  * the backward pass is explicit: `model.backward()` after the three loss methods (reference: tf.gradients,
+    utils/optimization.py:176).
+Every tensor is a CUDA tensor; all arithmetic runs in libmerlot_b200.so -- PyTorch only owns memory and streams.
+There is no CPU fallback: without the library (or without a GPU) construction raises.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .params import ParamStore
+
+MASK = 1  # utils/encode/encoder.py:16-22
+PADDING = 0
+START = 2
+
+_SITE_VIT, _SITE_LANGONLY, _SITE_JOINT, _SITE_EMB_LO, _SITE_EMB_J = 0, 100, 200, 300, 301
+
+
+def get_shape_list_rank(t: torch.Tensor, expected_rank, name="tensor"):
+    """utils/model_utils.py:29-56 assert_rank: ValueError on rank mismatch."""
+    ranks = expected_rank if isinstance(expected_rank, (list, tuple)) else [expected_rank]
+    if t.dim() not in ranks:
+        raise ValueError("For the tensor `%s`, the actual rank `%d` (shape = %s) is not equal to the expected rank `%s`" %
+                         (name, t.dim(), str(tuple(t.shape)), str(expected_rank)))
+    return list(t.shape)
+
+
+class _Buffers:
+    """Named device buffers cached on the ParamStore so pointers stay stable across steps (CUDA-graph friendly)."""
+
+    def __init__(self, store: ParamStore):
+        if not hasattr(store, "_bufs"):
+            store._bufs = {}
+        self.d = store._bufs
+        self.dev = store.device
+
+    def get(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.d.get(key)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.dev) if zero else torch.empty(shape, dtype=dtype, device=self.dev)
+            self.d[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+
+def _layer_params(store: ParamStore, scope: str, layers: int):
+    key = ("_lp", scope, layers)
+    if key in store._bufs:
+        return store._bufs[key]
+    arr = (L.LayerParams * layers)()
+    for l in range(layers):
+        ls = f"{scope}/layer{l:02d}"
+        lp = arr[l]
+        for field, name, bf in (("ln1_gamma", "LayerNorm_attn_ln0/gamma", 0), ("ln1_beta", "LayerNorm_attn_ln0/beta", 0),
+                                ("w_qkv", "qkv/kernel", 1), ("b_qkv", "qkv/bias", 0),
+                                ("w_o", "context_projection_layer/kernel", 1), ("b_o", "context_projection_layer/bias", 0),
+                                ("ln2_gamma", "LayerNorm_mlp_ln0/gamma", 0), ("ln2_beta", "LayerNorm_mlp_ln0/beta", 0),
+                                ("w_1", "intermediate/kernel", 1), ("b_1", "intermediate/bias", 0),
+                                ("w_2", "output/kernel", 1), ("b_2", "output/bias", 0)):
+            full = f"{ls}/{name}"
+            setattr(lp, field, (store.W(full) if bf else store.P(full)).data_ptr())
+            setattr(lp, "g_" + field, store.G(full).data_ptr())
+    store._bufs[key] = arr
+    return arr
+
+
+class _Stack:
+    """One transformer stack invocation (utils/transformer.py:171-247) through merlot_stack_forward/backward."""
+
+    def __init__(self, store, bufs, tag, scope, layers, B, S, valid, h_in, cfg, dropout_p, seed, site, save, colsum=None):
+        H, I, heads = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_attention_heads"]
+        if H % heads != 0 or H // heads != 64:
+            raise ValueError("passed in a tensor of shape {} when size_per_head={} and num_attention_heads={}".format(
+                (B * S, H), H // max(heads, 1), heads) + " (this build provides size_per_head=64 only)")
+        d = L.StackDesc()
+        d.B, d.S, d.H, d.I, d.heads, d.layers = B, S, H, I, heads, layers
+        self._lp = _layer_params(store, scope, layers)
+        d.layer_params = self._lp
+        fg, fb = f"{scope}/LayerNorm_ln_final/gamma", f"{scope}/LayerNorm_ln_final/beta"
+        d.final_gamma, d.final_beta = store.P(fg).data_ptr(), store.P(fb).data_ptr()
+        d.d_final_gamma, d.d_final_beta = store.G(fg).data_ptr(), store.G(fb).data_ptr()
+        d.valid = valid.data_ptr() if valid is not None else None
+        d.h_in = h_in.data_ptr()
+        self.y = bufs.get(f"{tag}.y", (B * S, H), torch.bfloat16)
+        d.y = self.y.data_ptr()
+        d.save_for_backward = int(save)
+        d.hidden_dropout_p = float(dropout_p)
+        d.attention_dropout_p = float(cfg.get("attention_probs_dropout_prob", 0.0) or 0.0)
+        d.dropout_seed, d.dropout_site_base = seed, site
+        self.arena = bufs.get(f"{tag}.act", (L.lib().merlot_stack_activation_bytes(C.byref(d)),), torch.uint8)
+        d.act_arena = self.arena.data_ptr()
+        d.attn_colsum = colsum.data_ptr() if colsum is not None else None
+        self.d, self.bufs, self.tag, self.keep = d, bufs, tag, (valid, h_in, colsum)
+
+    def forward(self):
+        L.check(L.lib().merlot_stack_forward(C.byref(self.d), ops._stream()))
+        return self.y
+
+    def backward(self, dy, dh_in):
+        d = self.d
+        scratch = self.bufs.get("stack.scratch", (L.lib().merlot_stack_scratch_bytes(C.byref(d)),), torch.uint8)
+        d.dy, d.dh_in, d.scratch = dy.data_ptr(), dh_in.data_ptr(), scratch.data_ptr()
+        L.check(L.lib().merlot_stack_backward(C.byref(d), ops._stream()))
+        return dh_in
+
+
+class MerlotModel(object):
+    def __init__(self, config, is_training, use_tpu, image, input_ids, mask_input=False, shuffled_idx_img=None,
+                 img_mask=None, log_attention_probs=True, *, params: ParamStore, mask_draws: Optional[Dict] = None,
+                 mask_override: Optional[Dict] = None, dropout_seed: int = 0, save_for_backward: Optional[bool] = None,
+                 dist=None):
+        """Arguments as model/modeling.py:48-66.  `use_tpu` is accepted and ignored (it only selects one-hot vs gather
+        embedding lookups in the reference, utils/model_utils.py:259-263 -- same values either way)."""
+        self.config = copy.deepcopy(config)
+        self.is_training = is_training
+        self.use_tpu = use_tpu
+        self.store = params
+        self.dist = dist
+        cfg = self.config
+        if not image.is_cuda or not input_ids.is_cuda:
+            raise L.MerlotError(L.MERLOT_EINVAL, "MerlotModel needs CUDA tensors: merlot_b200 has no CPU fallback")
+        if not cfg.get("use_bfloat16", False):
+            raise NotImplementedError("use_bfloat16: False (fp32 activations) is not provided; every shipped config sets True")
+        if cfg.get("num_imgs", 1) != 1 or cfg.get("num_texts", 1) != 1 or img_mask is not None:
+            raise NotImplementedError("num_imgs / num_texts / img_mask (VCR path, model/modeling.py:106-122) not provided yet")
+        if cfg.get("disable_pairwise_lang_attn", False):
+            raise NotImplementedError("disable_pairwise_lang_attn (model/modeling.py:160-168) not provided yet")
+        if not cfg.get("share_params", True):
+            raise NotImplementedError("share_params: False (separate langonly_encoder, model/modeling.py:361) not provided yet")
+
+        input_ids_shape = get_shape_list_rank(input_ids, [2, 3], "input_ids")
+        if len(input_ids_shape) == 2:  # :72-77
+            self.num_chunks = 1
+            self.num_chunks_in_group = 1
+            self.batch_size, self.lang_chunk_length = input_ids_shape
+            self.input_ids = input_ids[:, None]
+        else:
+            self.input_ids = input_ids
+            self.batch_size, self.num_chunks, self.lang_chunk_length = input_ids_shape
+            self.num_chunks_in_group = cfg.get("num_chunks_in_group", self.num_chunks)
+            assert self.num_chunks % self.num_chunks_in_group == 0  # :82
+        self.input_ids = self.input_ids.to(torch.int32).contiguous()
+        self.num_imgs = cfg.get("num_imgs", 1)
+        self.num_texts = cfg.get("num_texts", 1)
+        self.img_batch_size = self.batch_size // self.num_texts
+        if not is_training:  # :88-90
+            cfg["hidden_dropout_prob"] = 0.0
+            cfg["attention_probs_dropout_prob"] = 0.0
+        self._save = bool(is_training) if save_for_backward is None else bool(save_for_backward)
+        self._seed = int(dropout_seed)
+        self._bufs = _Buffers(params)
+        self._mask_input = mask_input
+        self._log_attention_probs = log_attention_probs
+        self._forward(image, shuffled_idx_img, mask_draws, mask_override)
+
+    # ---- shapes (:226-260) ----
+    @property
+    def hidden_size(self):
+        return self.config["hidden_size"]
+
+    @property
+    def vocab_size(self):
+        return self.config["vocab_size"]
+
+    @property
+    def B(self):
+        return self.batch_size * (self.num_chunks // self.num_chunks_in_group)
+
+    @property
+    def L(self):
+        return self.lang_chunk_length * self.num_chunks_in_group
+
+    @property
+    def viz_chunk_length(self):
+        return self.vision_transformer_info["num_h"] * self.vision_transformer_info["num_w"] + 1
+
+    @property
+    def P(self):
+        return self.viz_chunk_length * self.num_chunks_in_group
+
+    @property
+    def dropout_prob(self):
+        return self.config["hidden_dropout_prob"]
+
+    @property
+    def use_bfloat16(self):
+        return self.config["use_bfloat16"]
+
+    @property
+    def word_embedding_table(self):
+        return self.store.P("word_embeddings/word_embeddings")
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _forward(self, image, shuffled_idx_img, mask_draws, mask_override):
+        cfg, st, bf = self.config, self.store, self._bufs
+        H = self.hidden_size
+        dev = st.device
+        get_shape_list_rank(image, 4, "image")
+        N, h0, w0, c3 = image.shape
+        Pp = cfg["patch_size"]
+        assert h0 % Pp == 0  # utils/vision_transformer.py:189
+        assert w0 % Pp == 0  # :190
+        if c3 != 3:
+            raise ValueError(f"image must be [N,h,w,3], got {tuple(image.shape)}")
+        if N != self.batch_size * self.num_chunks:
+            raise ValueError(f"image batch {N} != batch_size*num_chunks {self.batch_size * self.num_chunks}")
+        ncls = cfg.get("num_cls_emb", 2)
+        h1, w1 = h0 // Pp, w0 // Pp
+        np_ = h1 * w1
+        Sv = np_ + ncls
+        Mv = N * Sv
+        sp = cfg["spatial_pool_size"]
+        h2, w2 = (h1 // sp, w1 // sp) if sp > 1 else (h1, w1)
+        self.vision_transformer_info = {"num_h": h2, "num_w": w2}
+        vcl, ncg, B, Lj = self.viz_chunk_length, self.num_chunks_in_group, self.B, self.L
+        Pz = self.P
+        Sj = Pz + Lj
+        self._dims = dict(N=N, h1=h1, w1=w1, np=np_, ncls=ncls, Sv=Sv, Mv=Mv, sp=max(sp, 1), h2=h2, w2=w2, vcl=vcl, Pz=Pz,
+                          Sj=Sj, Kp=Pp * Pp * 3)
+        train = self.is_training
+        p_hid = float(cfg["hidden_dropout_prob"] or 0.0)
+        p_vit = float(cfg.get("vit_hidden_dropout_prob", cfg["hidden_dropout_prob"]) or 0.0) if train else 0.0
+        vt = "vision_backbone/vision_transformer"
+
+        # ---- ViT (utils/vision_transformer.py:173-274) ----
+        img = image if image.dtype == torch.bfloat16 else image.to(torch.bfloat16)
+        img = img.contiguous()
+        A = bf.get("vit.A", (N * np_, Pp * Pp * 3), torch.bfloat16)
+        ops.patch_im2col(img, A, Pp)
+        patch = bf.get("vit.patch", (N * np_, H), torch.float32)
+        ops.gemm(A, st.W(f"{vt}/conv2d/kernel"), b_mn_major=True, bias=st.P(f"{vt}/conv2d/bias"), out=patch)
+        xsum_v = bf.get("vit.xsum", (Mv, H), torch.float32)
+        ops.vit_assemble_fwd(patch, st.P(f"{vt}/pos_embs/pos_embs"), st.P(f"{vt}/pos_embs/cls_emb"), xsum_v, N, h1, w1, ncls, H)
+        h0_v = bf.get("vit.h0", (Mv, H), torch.bfloat16)
+        mean_v, rstd_v = bf.get("vit.mean0", (Mv,), torch.float32), bf.get("vit.rstd0", (Mv,), torch.float32)
+        ops.layernorm_fwd(xsum_v, h0_v, st.P(f"{vt}/LayerNorm_ctx_patches_pre_ln/gamma"),
+                          st.P(f"{vt}/LayerNorm_ctx_patches_pre_ln/beta"), mean_v, rstd_v)
+        self._vit = _Stack(st, bf, "vit", vt, cfg.get("num_vision_transformer_hidden_layers", cfg["num_hidden_layers"]), N, Sv,
+                           None, h0_v, cfg, p_vit, self._seed, _SITE_VIT, self._save)
+        hv = self._vit.forward()
+
+        # ---- viz tokens (:95-133) ----
+        if shuffled_idx_img is None:
+            img_idx = bf.get("img_idx.arange", (N,), torch.int32)
+            img_idx.copy_(torch.arange(ncg, dtype=torch.int32, device=dev).repeat(B))
+            self._shuffled = None
+        else:
+            assert self.num_imgs == 1 and self.num_texts == 1  # :319-320
+            img_idx = shuffled_idx_img.reshape(-1).to(torch.int32).contiguous()
+            if img_idx.numel() != N:
+                raise ValueError(f"shuffled_idx_img has {img_idx.numel()} entries, expected B*num_chunks_in_group = {N}")
+        self._img_idx = img_idx
+        xsum_z = bf.get("viz.xsum", (B * Pz, H), torch.float32)
+        self.img_trg_h = bf.get("viz.img_trg", (N, H), torch.float32)
+        ops.viz_assemble_fwd(hv, st.P("vision_backbone/img_idx_pe"), img_idx, st.P("vision_backbone/final_pe/pos_embs"),
+                             st.P("vision_backbone/final_pe/cls_emb"), xsum_z, self.img_trg_h, N, h1, w1, ncls, max(sp, 1), H)
+        joint_in = bf.get("joint.in", (B * Sj, H), torch.bfloat16)
+        mean_z, rstd_z = bf.get("viz.mean", (B * Pz,), torch.float32), bf.get("viz.rstd", (B * Pz,), torch.float32)
+        ops.layernorm_fwd(xsum_z, joint_in, st.P("vision_backbone/LayerNorm_final_ln/gamma"),
+                          st.P("vision_backbone/LayerNorm_final_ln/beta"), mean_z, rstd_z, remap=(Pz, Sj, 0))
+
+        # ---- language-only encoder + masking (:135-139) ----
+        ids_bl = self.input_ids.reshape(B, Lj)
+        if self._mask_input:
+            self._langonly_reps()
+            if mask_override is not None:
+                self.lang_mask_info = {"masked_ids": mask_override["masked_ids"].to(dev).to(torch.int32).reshape(B, Lj).contiguous(),
+                                       "masked_idx": mask_override["masked_idx"].to(dev).to(torch.int32).contiguous()}
+            else:
+                self.lang_mask_info = self.mask_inputs(mask_draws)
+            ids_to_use = self.lang_mask_info["masked_ids"].reshape(B, Lj)
+        else:
+            ids_to_use = ids_bl
+        self._ids_j = ids_to_use.contiguous()
+
+        # ---- joint encoder (:143-184) ----
+        self._embed_words_into(self._ids_j, "position_embeddings", "emb_j", _SITE_EMB_J, joint_in, remap=(Lj, Sj, Pz))
+        valid_j = bf.get("joint.valid", (B * Sj,), torch.uint8)
+        ops.joint_valid(self._ids_j, valid_j, B, Pz, Lj)
+        self._joint = _Stack(st, bf, "joint", "encoder", cfg["num_hidden_layers"], B, Sj, valid_j, joint_in, cfg,
+                             p_hid if train else 0.0, self._seed, _SITE_JOINT, self._save)
+        self._y_j = self._joint.forward()
+        self.encoder_info = {"hidden_state": self._y_j.view(B, Sj, H)}
+        self._hidden_f32 = {}
+        self.encoder_pieces = [{"name": "viz", "start": 0, "end": Pz}, {"name": "lang", "start": Pz, "end": Sj}]
+        self._heads = {}
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _embed_words_into(self, ids_2d, norm_scope_name, tag, site, out, remap):
+        """embed_words (:262-297): E[ids] + Pos[0:L] -> LN embed_norm -> dropout -> bf16, written into `out` rows."""
+        st, bf, cfg = self.store, self._bufs, self.config
+        H = self.hidden_size
+        R, Lseq = ids_2d.numel(), ids_2d.shape[1]
+        if Lseq > cfg["max_position_embeddings"]:  # tf.assert_less_equal, utils/model_utils.py:282
+            raise ValueError(f"sequence length {Lseq} exceeds max_position_embeddings {cfg['max_position_embeddings']}")
+        xsum = bf.get(f"{tag}.xsum", (R, H), torch.float32)
+        ops.embed_fwd(ids_2d, st.P("word_embeddings/word_embeddings"), st.P(f"{norm_scope_name}/position_embeddings"), xsum, Lseq)
+        mean, rstd = bf.get(f"{tag}.mean", (R,), torch.float32), bf.get(f"{tag}.rstd", (R,), torch.float32)
+        p = float(self.dropout_prob or 0.0) if self.is_training else 0.0
+        ops.layernorm_fwd(xsum, out, st.P(f"{norm_scope_name}/LayerNorm_embed_norm/gamma"),
+                          st.P(f"{norm_scope_name}/LayerNorm_embed_norm/beta"), mean, rstd, rows=R, remap=remap,
+                          dropout=(p, self._seed, site))
+        return xsum, mean, rstd
+
+    def embed_words(self, input_ids_2d, norm_scope_name="position_embeddings", reuse=None):
+        """Public mirror of :262-297; returns bf16 [B, L, H]."""
+        get_shape_list_rank(input_ids_2d, 2, "input_ids_2d")
+        ids = input_ids_2d.to(torch.int32).contiguous()
+        out = torch.empty((ids.numel(), self.hidden_size), dtype=torch.bfloat16, device=ids.device)
+        self._embed_words_into(ids, norm_scope_name, f"emb_pub.{norm_scope_name}", _SITE_EMB_J, out, (0, 0, 0))
+        return out.view(ids.shape[0], ids.shape[1], -1)
+
+    def _langonly_reps(self):
+        """langonly_reps (:339-379)."""
+        cfg, st, bf = self.config, self.store, self._bufs
+        H = self.hidden_size
+        if "langonly_num_chunks_in_group" in cfg:
+            g = cfg["langonly_num_chunks_in_group"]
+            ng = self.num_chunks // g
+            assert ng > 0
+            assert self.num_chunks % g == 0
+            ids = self.input_ids.reshape(self.batch_size * ng, self.lang_chunk_length * g)
+        else:
+            ids = self.input_ids.reshape(self.batch_size, self.lang_chunk_length * self.num_chunks)
+        ids = ids.contiguous()
+        Blo, Llo = ids.shape
+        self._ids_lo = ids
+        h0 = bf.get("lo.h0", (Blo * Llo, H), torch.bfloat16)
+        self._embed_words_into(ids, "langonly_embeddings", "emb_lo", _SITE_EMB_LO, h0, (0, 0, 0))
+        valid = bf.get("lo.valid", (Blo * Llo,), torch.uint8)
+        ops.ids_valid(ids, valid)
+        summ = bf.get("lo.attn_summ", (Blo * Llo,), torch.float32, zero=True)
+        p = float(self.dropout_prob or 0.0) if self.is_training else 0.0
+        self._lo = _Stack(st, bf, "lo", "encoder", cfg["num_lang_transformer_hidden_layers"], Blo, Llo, valid, h0, cfg, p,
+                          self._seed, _SITE_LANGONLY, self._save, colsum=summ)
+        y = self._lo.forward()
+        nch = self.batch_size * self.num_chunks
+        pool_idx = bf.get("lo.pool_idx", (nch,), torch.int32)
+        pool_idx.copy_(torch.arange(nch, dtype=torch.int32, device=st.device) * self.lang_chunk_length)
+        self._pool_idx_lo = pool_idx
+        self.lang_trg_h = bf.get("lo.lang_trg", (nch, H), torch.float32)
+        ops.gather_rows(y, pool_idx, self.lang_trg_h)
+        # attention_summs of mask_inputs (:428-431): sum over (layers, queries) of head-mean probabilities, as [B, L]
+        self.lang_transformer_info = {"hidden_state": y.view(Blo, Llo, H), "attention_summs": summ.view(self.B, self.L)}
+        return self.lang_trg_h, self.lang_transformer_info
+
+    def langonly_reps(self):
+        return self.lang_trg_h, self.lang_transformer_info
+
+    def mask_inputs(self, draws: Optional[Dict] = None):
+        """mask_inputs (:381-489) on device; `draws` injects the reference's five tf.random tensors."""
+        cfg, bf = self.config, self._bufs
+        B, Lj = self.B, self.L
+        dev = self.store.device
+        topk_perc = cfg.get("masking_use_topk_from_attn_perc", 0.20)
+        choose_topk_prob = cfg.get("masking_choose_topk_prob", 0.5)
+        masking_rate = cfg.get("masking_rate", 0.2)
+        do_spanbert = cfg.get("masking_do_spanbert", True)
+        span_probs = cfg.get("masking_spanbert_len_probs", [0.625, 0.25, 0.125])
+        use_attn = cfg.get("masking_use_attn", True)
+        num_topk = int(Lj * topk_perc)
+        num_to_mask = int(Lj * masking_rate)
+        nontopk_val = 0.01
+        topk_val = nontopk_val * choose_topk_prob * (1.0 - topk_perc) / (topk_perc * (1.0 - choose_topk_prob))  # :418-419
+        if use_attn:
+            w = torch.tensor([1.0, 0.0]) * np.float32(topk_val - nontopk_val) + np.float32(nontopk_val)  # :437
+            logw = torch.log(w)
+            consts = (float(np.float32(topk_val - nontopk_val)), float(np.float32(nontopk_val)), float(logw[0]), float(logw[1]),
+                      float(w.max()))
+        else:
+            consts = (0.0, 1.0, 0.0, 0.0, 1.0)
+        if draws is None:
+            draws = self.make_mask_draws(B, Lj, num_to_mask, self.vocab_size, span_probs, dev, seed=self._seed)
+        draws = {k: v.to(dev).contiguous() for k, v in draws.items()}
+        masked_ids = bf.get("mask.ids", (B, Lj), torch.int32)
+        masked_idx = bf.get("mask.idx", (B, num_to_mask), torch.int32)
+        summ = self.lang_transformer_info["attention_summs"] if use_attn else None
+        ops.mask_inputs(self.input_ids.reshape(B, Lj), summ, draws, masked_ids, masked_idx, None, num_topk, num_to_mask,
+                        do_spanbert, MASK, consts)
+        return {"masked_ids": masked_ids.view(self.input_ids.shape), "masked_idx": masked_idx}
+
+    @staticmethod
+    def make_mask_draws(B, Lj, num_to_mask, vocab_size, span_probs, device, seed=0):
+        """The tf.random.* draws of mask_inputs (:445-481) from a torch generator."""
+        g = torch.Generator(device="cpu").manual_seed(1234567 + seed)
+        u = torch.rand(B, Lj, generator=g).clamp_(1e-9, 1.0 - 1e-7)
+        probs = torch.tensor(span_probs, dtype=torch.float32)
+        return {
+            "gumbel": (-torch.log(-torch.log(u))).float(),
+            "span_lower": torch.multinomial(probs, B * num_to_mask, True, generator=g).reshape(B, num_to_mask).int(),
+            "span_upper": torch.multinomial(probs, B * num_to_mask, True, generator=g).reshape(B, num_to_mask).int(),
+            "option": torch.multinomial(torch.tensor([0.1, 0.8, 0.1]), B * Lj, True, generator=g).int(),
+            "rand_ids": torch.randint(100, vocab_size, (B * Lj,), generator=g).int(),
+        }
+
+    # ---- attributes the callers read (:176-203) ----
+    @property
+    def encoder_hidden_states(self):
+        """{'viz': fp32 [B,P,H], 'lang': fp32 [B,L,H]} (:176-184)."""
+        if not self._hidden_f32:
+            H, B, Sj, Pz = self.hidden_size, self.B, self._dims["Sj"], self._dims["Pz"]
+            y3 = self._y_j.view(B, Sj, H)
+            for name, sl in (("viz", slice(0, Pz)), ("lang", slice(Pz, Sj))):
+                piece = y3[:, sl].contiguous()
+                out = torch.empty(piece.shape, dtype=torch.float32, device=piece.device)
+                ops.cast_bf16_to_f32(piece, out)
+                self._hidden_f32[name] = out
+        return self._hidden_f32
+
+    @property
+    def attention_log(self):
+        raise NotImplementedError("attention_log metrics (model/modeling.py:186-203) are not provided yet; they are "
+                                  "logging-only and carry no gradient")
+
+    # ---------------------------------------------------------------------------------------------------------
+    # heads
+    # ---------------------------------------------------------------------------------------------------------
+    def _dense_f32(self, x_bf16, scope, out):
+        """tf.layers.dense on a small head tensor: bf16 operands, fp32 accumulate/output (+bias)."""
+        st = self.store
+        return ops.gemm(x_bf16, st.W(f"{scope}/kernel"), b_mn_major=True, bias=st.P(f"{scope}/bias"), out=out)
+
+    def _mlp_ln(self, tag, x_bf16, dense_scope, ln_scope, R, Hout):
+        """dense + gelu -> layer_norm (the repeated head pattern, e.g. :28-35, :208-215, :582-589). Returns bf16 output."""
+        st, bf = self.store, self._bufs
+        pre = bf.get(f"{tag}.pre", (R, Hout), torch.float32)
+        self._dense_f32(x_bf16, dense_scope, pre)
+        act = bf.get(f"{tag}.act", (R, Hout), torch.float32)
+        ops.gelu_f32(pre, act)
+        an = bf.get(f"{tag}.an", (R, Hout), torch.bfloat16)
+        mean, rstd = bf.get(f"{tag}.mean", (R,), torch.float32), bf.get(f"{tag}.rstd", (R,), torch.float32)
+        ops.layernorm_fwd(act, an, st.P(f"{ln_scope}/gamma"), st.P(f"{ln_scope}/beta"), mean, rstd, rows=R)
+        return dict(x=x_bf16, pre=pre, act=act, an=an, mean=mean, rstd=rstd, dense=dense_scope, ln=ln_scope, R=R, Hout=Hout, tag=tag)
+
+    def _mlp_ln_bwd(self, t, d_an_f32, need_dx=True):
+        """Backward of _mlp_ln: accumulates parameter grads, returns d_x fp32 [R, Hin]."""
+        st, bf = self.store, self._bufs
+        R, Hout, tag = t["R"], t["Hout"], t["tag"]
+        d_act = bf.get(f"{tag}.d_act", (R, Hout), torch.float32)
+        ops.layernorm_bwd(d_an_f32, t["act"], t["mean"], t["rstd"], st.P(f"{t['ln']}/gamma"), d_act, st.G(f"{t['ln']}/gamma"),
+                          st.G(f"{t['ln']}/beta"), rows=R)
+        d_pre = bf.get(f"{tag}.d_pre", (R, Hout), torch.float32)
+        ops.gelu_bwd_f32(d_act, t["pre"], d_pre)
+        return self._dense_bwd(tag, t["x"], t["dense"], d_pre, need_dx)
+
+    def _dense_bwd(self, tag, x_bf16, scope, dy_f32, need_dx=True):
+        st, bf = self.store, self._bufs
+        R, N = dy_f32.shape
+        Kin = x_bf16.shape[1]
+        ops.bias_grad(dy_f32, st.G(f"{scope}/bias"), rows=R, N=N)
+        dyb = bf.get(f"{tag}.dyb.{scope}", (R, N), torch.bfloat16)
+        ops.cast_f32_to_bf16(dy_f32, dyb)
+        ops.gemm(x_bf16, dyb, a_mn_major=True, b_mn_major=True, out=st.G(f"{scope}/kernel"), atomic=True, M=Kin, N=N, K=R)
+        if not need_dx:
+            return None
+        dx = bf.get(f"{tag}.dx.{scope}", (R, Kin), torch.float32)
+        ops.gemm(dyb, st.W(f"{scope}/kernel"), out=dx, M=R, N=Kin, K=N)
+        return dx
+
+    def lm_head(self, hidden_state):
+        """lm_head (:205-224) on bf16 rows [R,H]; returns fp32 logits [R, ldV] (columns >= vocab_size are padding)."""
+        return self._lm_head("lm_pub", hidden_state.contiguous())["logits"][:, :self.vocab_size]
+
+    def _lm_head(self, tag, pooled):
+        cfg, st, bf = self.config, self.store, self._bufs
+        R, H, V = pooled.shape[0], self.hidden_size, self.vocab_size
+        t = {}
+        hn = pooled
+        if cfg.get("do_projection", False):
+            t = self._mlp_ln(f"{tag}.proj", pooled, "lm_head/projection", "lm_head/LayerNorm", R, H)
+            hn = t["an"]
+        ldV = (V + 63) // 64 * 64
+        logits = bf.get(f"{tag}.logits", (R, ldV), torch.float32)
+        bias = st.P("lm_head/output_bias") if cfg.get("do_bias", False) else None
+        ops.gemm(hn, st.W("word_embeddings/word_embeddings"), bias=bias, out=logits, M=R, N=V, K=H)
+        return dict(proj=t, hn=hn, logits=logits, ldV=ldV)
+
+    def mask_loss(self):
+        """mask_loss (:528-551).  Returns (loss, {'loss','acc'}) as 0-d CUDA tensors."""
+        bf = self._bufs
+        B, Lj, V = self.B, self.L, self.vocab_size
+        k = self.lang_mask_info["masked_idx"].shape[1]
+        nm = B * k
+        rows = bf.get("mlm.rows", (nm,), torch.int32)
+        targets = bf.get("mlm.targets", (nm,), torch.int32)
+        ops.mlm_index(self.input_ids.reshape(B, Lj), self.lang_mask_info["masked_idx"], rows, targets, B, Lj, k, self._dims["Pz"])
+        pooled = bf.get("mlm.pooled", (nm, self.hidden_size), torch.bfloat16)
+        ops.gather_rows(self._y_j, rows, pooled)
+        hd = self._lm_head("mlm", pooled)
+        per, lse, corr = (bf.get(f"mlm.{n}", (nm,), torch.float32) for n in ("l", "lse", "corr"))
+        ops.softmax_ce_fwd(hd["logits"], targets, V, per, lse, corr)
+        out2 = bf.get("mlm.out", (2,), torch.float32)
+        coeff = bf.get("mlm.coeff", (nm,), torch.float32)
+        ops.weighted_loss(per, corr, None, targets, 1, 1.0, out2, coeff)
+        self._heads["mlm"] = dict(rows=rows, targets=targets, pooled=pooled, lse=lse, coeff=coeff, nm=nm, **hd)
+        return out2[0], {"loss": out2[0], "acc": out2[1]}
+
+    def _mask_loss_bwd(self, d_yj):
+        st, bf = self.store, self._bufs
+        h = self._heads["mlm"]
+        V, H, nm, ldV = self.vocab_size, self.hidden_size, h["nm"], h["ldV"]
+        dlog = bf.get("mlm.dlogits", (nm, ldV), torch.bfloat16)
+        ops.softmax_ce_bwd(h["logits"], h["targets"], V, h["lse"], h["coeff"], dlog)
+        if self.config.get("do_bias", False):
+            gb = st.G("lm_head/output_bias")
+            gb_pad = st.g[st.entries["lm_head/output_bias"].offset:st.entries["lm_head/output_bias"].offset + ldV]
+            ops.bias_grad(dlog, gb_pad, rows=nm, N=ldV)
+        # tied embedding: dE += dlogits^T hn ; d_hn = dlogits E
+        ops.gemm(dlog, h["hn"], a_mn_major=True, b_mn_major=True, out=st.G("word_embeddings/word_embeddings"), atomic=True,
+                 M=V, N=H, K=nm)
+        d_hn = bf.get("mlm.d_hn", (nm, H), torch.float32)
+        ops.gemm(dlog, st.W("word_embeddings/word_embeddings"), b_mn_major=True, out=d_hn, M=nm, N=H, K=V)
+        d_pooled = self._mlp_ln_bwd(h["proj"], d_hn) if h["proj"] else d_hn
+        ops.scatter_add_rows(d_pooled, h["rows"], d_yj)
+
+    def _tower(self, tag, x_f32, name):
+        """project_and_norm (:18-44) under scope 'contrastive'."""
+        cfg, bf = self.config, self._bufs
+        n, H = x_f32.shape
+        Cs = cfg.get("contrastive_size", H)
+        xb = bf.get(f"{tag}.xb", (n, H), torch.bfloat16)
+        ops.cast_f32_to_bf16(x_f32, xb)
+        t = {}
+        inp = xb
+        if cfg.get("do_projection", False):
+            t = self._mlp_ln(f"{tag}.inter", xb, f"contrastive/{name}_intermediate", f"contrastive/LayerNorm_{name}_ln", n, Cs)
+            inp = t["an"]
+        proj = bf.get(f"{tag}.proj", (n, Cs), torch.float32)
+        self._dense_f32(inp, f"contrastive/{name}", proj)
+        feat = bf.get(f"{tag}.feat", (n, Cs), torch.float32)
+        inv = bf.get(f"{tag}.inv", (n,), torch.float32)
+        ops.l2norm_fwd(proj, feat, inv)
+        return dict(tag=tag, name=name, xb=xb, inter=t, inp=inp, feat=feat, inv=inv, n=n, Cs=Cs)
+
+    def _tower_bwd(self, t, d_feat):
+        bf = self._bufs
+        d_proj = bf.get(f"{t['tag']}.d_proj", (t["n"], t["Cs"]), torch.float32)
+        ops.l2norm_bwd(d_feat, t["feat"], t["inv"], d_proj)
+        d_inp = self._dense_bwd(t["tag"], t["inp"], f"contrastive/{t['name']}", d_proj)
+        return self._mlp_ln_bwd(t["inter"], d_inp) if t["inter"] else d_inp
+
+    def contrastive_loss(self):
+        """contrastive_loss (:491-526).  Multi-GPU: features are all-gathered over the data-parallel group
+        (tpu_cross_replica_stack, utils/model_utils.py:673-707) and labels are offset by rank*N (:519)."""
+        cfg, bf = self.config, self._bufs
+        lang = self._tower("ctr.lang", self.lang_trg_h, "lang_proj")
+        viz = self._tower("ctr.viz", self.img_trg_h, "viz_proj")
+        n, Cs = lang["n"], lang["Cs"]
+        world, rank = (self.dist.world, self.dist.rank) if self.dist is not None else (1, 0)
+        if world > 1:
+            all_lang, all_viz = self.dist.all_gather_rows(lang["feat"]), self.dist.all_gather_rows(viz["feat"])
+        else:
+            all_lang, all_viz = lang["feat"], viz["feat"]
+        temp = cfg.get("contrast_temp", 0.05)
+        coef = cfg.get("contrast_coef", 1.0)
+        labels = bf.get("ctr.labels", (n,), torch.int32)
+        labels.copy_(torch.arange(n, dtype=torch.int32, device=labels.device) + rank * n)
+        nW = n * world
+        outs = {}
+        info = dict(lang=lang, viz=viz, all_lang=all_lang, all_viz=all_viz, labels=labels, nW=nW, temp=temp, dirs={})
+        for name, x, y in (("lang_to_viz", lang["feat"], all_viz), ("viz_to_lang", viz["feat"], all_lang)):
+            logits = bf.get(f"ctr.{name}.logits", (n, nW), torch.float32)
+            ops.small_gemm(x, Cs, 1, y, Cs, 1, logits, n, nW, Cs, alpha=1.0 / temp)
+            per, lse = bf.get(f"ctr.{name}.l", (n,), torch.float32), bf.get(f"ctr.{name}.lse", (n,), torch.float32)
+            ops.softmax_ce_fwd(logits, labels, nW, per, lse, None)
+            out2 = bf.get(f"ctr.{name}.out", (2,), torch.float32)
+            coeff = bf.get(f"ctr.{name}.coeff", (n,), torch.float32)
+            ops.weighted_loss(per, None, None, None, 0, coef / 2.0, out2, coeff)
+            outs[name] = out2[0]
+            info["dirs"][name] = dict(logits=logits, lse=lse, coeff=coeff)
+        loss_all = bf.get("ctr.loss_all", (1,), torch.float32)
+        ops.axpby(bf.get("ctr.lang_to_viz.out", (2,), torch.float32)[:1], loss_all, coef / 2.0, 0.0)
+        ops.axpby(bf.get("ctr.viz_to_lang.out", (2,), torch.float32)[:1], loss_all, coef / 2.0, 1.0)
+        outs["loss_all"] = loss_all[0]
+        self._heads["ctr"] = info
+        return loss_all[0], outs
+
+    def _contrastive_bwd(self, d_lang_trg, d_img_trg):
+        bf = self._bufs
+        c = self._heads["ctr"]
+        lang, viz, nW, temp = c["lang"], c["viz"], c["nW"], c["temp"]
+        n, Cs = lang["n"], lang["Cs"]
+        world = self.dist.world if self.dist is not None else 1
+        d_feat = {"lang": bf.get("ctr.d_feat.lang", (n, Cs), torch.float32), "viz": bf.get("ctr.d_feat.viz", (n, Cs), torch.float32)}
+        d_all = {"lang": bf.get("ctr.d_all.lang", (nW, Cs), torch.float32), "viz": bf.get("ctr.d_all.viz", (nW, Cs), torch.float32)}
+        for name, xk, yk, y_all in (("lang_to_viz", "lang", "viz", c["all_viz"]), ("viz_to_lang", "viz", "lang", c["all_lang"])):
+            d = c["dirs"][name]
+            dlog = bf.get(f"ctr.{name}.dlogits", (n, nW), torch.float32)
+            ops.softmax_ce_bwd(d["logits"], c["labels"], nW, d["lse"], d["coeff"], dlog)
+            x = c[xk]["feat"]
+            # d_x[i,c] = sum_j dlog[i,j] y_all[j,c] / temp
+            ops.small_gemm(dlog, nW, 1, y_all, 1, Cs, d_feat[xk], n, Cs, nW, alpha=1.0 / temp, beta=0.0)
+            # d_y_all[j,c] = sum_i dlog[i,j] x[i,c] / temp
+            ops.small_gemm(dlog, 1, nW, x, 1, Cs, d_all[yk], nW, Cs, n, alpha=1.0 / temp, beta=0.0)
+        for k in ("lang", "viz"):
+            # gradient of the gather = reduce-scatter(sum) of every rank's d_all (utils/model_utils.py:699-706)
+            mine = self.dist.reduce_scatter_rows(d_all[k]) if world > 1 else d_all[k]
+            ops.axpby(mine, d_feat[k], 1.0, 1.0)
+        dl = self._tower_bwd(lang, d_feat["lang"])
+        dv = self._tower_bwd(viz, d_feat["viz"])
+        ops.axpby(dl, d_lang_trg, 1.0, 1.0)
+        ops.axpby(dv, d_img_trg, 1.0, 1.0)
+
+    def _temporal_index(self):
+        bf, dev = self._bufs, self.store.device
+        B, n, Sj, Pz, vcl, Lc = self.B, self.num_chunks_in_group, self._dims["Sj"], self._dims["Pz"], self.viz_chunk_length, \
+            self.lang_chunk_length
+        key = ("_tidx", B, n, Sj, Pz, vcl, Lc)
+        if key not in bf.d:
+            b = torch.arange(B, device=dev)[:, None]
+            s = torch.arange(n, device=dev)[None]
+            idx_l = (b * Sj + Pz + s * Lc).reshape(-1).to(torch.int32)
+            idx_v = (b * Sj + s * vcl).reshape(-1).to(torch.int32)
+            bi = torch.arange(B, device=dev)[:, None, None]
+            i = torch.arange(n, device=dev)[None, :, None]
+            j = torch.arange(n, device=dev)[None, None, :]
+            idxA = (bi * n + i + 0 * j).reshape(-1).to(torch.int32)  # row b*n*n + i*n + j takes xa[b, i]   (:573-574)
+            idxB = (bi * n + j + 0 * i).reshape(-1).to(torch.int32)  # ... and xb[b, j]                       (:576-577)
+            bf.d[key] = (idx_l, idx_v, idxA, idxB)
+        return bf.d[key]
+
+    def allpairs_temporal_logits(self, xa, xb, scope_name="temporal_paired"):
+        """allpairs_temporal_logits (:553-596). xa, xb: [B, n, H] (fp32 or bf16). Returns fp32 logits [B*n*n, 4]."""
+        get_shape_list_rank(xa, 3, "xa")
+        B, n, H = xa.shape
+        assert list(xa.shape) == [B, self.num_chunks_in_group, self.hidden_size]
+        assert list(xb.shape) == [B, self.num_chunks_in_group, self.hidden_size]
+        xa2 = xa.reshape(B * n, H).to(torch.bfloat16).contiguous()
+        xb2 = xb.reshape(B * n, H).to(torch.bfloat16).contiguous()
+        return self._temporal_head(f"tmp_pub.{scope_name}", scope_name, xa2, xb2)["logits"][:, :4]
+
+    def _temporal_head(self, tag, scope, xa_bf16, xb_bf16):
+        st, bf = self.store, self._bufs
+        B, n, H = self.B, self.num_chunks_in_group, self.hidden_size
+        _, _, idxA, idxB = self._temporal_index()
+        R = B * n * n
+        hj = bf.get(f"{tag}.hj", (R, 2 * H), torch.bfloat16)
+        ops.gather_rows(xa_bf16, idxA, hj[:, :H], H=H)
+        ops.gather_rows(xb_bf16, idxB, hj[:, H:], H=H)
+        t = self._mlp_ln(f"{tag}.mlp", hj, f"{scope}/intermediate", f"{scope}/LayerNorm_ln0", R, H)
+        logits = bf.get(f"{tag}.logits", (R, 8), torch.float32)
+        self._dense_f32(t["an"], f"{scope}/logits", logits)
+        return dict(tag=tag, scope=scope, hj=hj, mlp=t, logits=logits, R=R)
+
+    def allpairs_temporal_labels(self, video_src_ids, shuffled_idx_img=None):
+        """allpairs_temporal_labels (:598-620)."""
+        bf = self._bufs
+        B, n = self.B, self.num_chunks_in_group
+        labels = bf.get("tmp.labels", (B * n * n,), torch.int32)
+        w = bf.get("tmp.w", (B * n * n,), torch.float32)
+        v = video_src_ids.reshape(B, n).to(torch.int32).contiguous()
+        s = (shuffled_idx_img if shuffled_idx_img is not None else torch.zeros_like(v)).reshape(B, n).to(torch.int32).contiguous()
+        ops.temporal_labels(v, s, labels, w, B, n)
+        self._tmp_w = w
+        return labels
+
+    def temporal_loss(self, shuffled_idx_img, video_src_ids):
+        """temporal_loss (:622-668)."""
+        cfg, bf = self.config, self._bufs
+        B, n, H = self.B, self.num_chunks_in_group, self.hidden_size
+        idx_l, idx_v, _, _ = self._temporal_index()
+        h_lang = bf.get("tmp.h_lang", (B * n, H), torch.bfloat16)
+        h_viz = bf.get("tmp.h_viz", (B * n, H), torch.bfloat16)
+        ops.gather_rows(self._y_j, idx_l, h_lang)
+        ops.gather_rows(self._y_j, idx_v, h_viz)
+        labels = self.allpairs_temporal_labels(video_src_ids, shuffled_idx_img)
+        w = self._tmp_w
+        coef = cfg.get("temporal_coef", 1.0)
+        use_vv = cfg.get("image_shuffle_prob", 0) > 0  # :664-665
+        info, heads = {}, {}
+        for name, xa, xb in (("lang_viz", h_lang, h_viz), ("viz_viz", h_viz, h_viz)):
+            hd = self._temporal_head(f"tmp.{name}", f"{name}_temporal", xa, xb)
+            R = hd["R"]
+            per, lse, corr = (bf.get(f"tmp.{name}.{k}", (R,), torch.float32) for k in ("l", "lse", "corr"))
+            ops.softmax_ce_fwd(hd["logits"], labels, 4, per, lse, corr)
+            out2 = bf.get(f"tmp.{name}.out", (2,), torch.float32)
+            coeff = bf.get(f"tmp.{name}.coeff", (R,), torch.float32)
+            ops.weighted_loss(per, corr, w, None, 0, coef, out2, coeff)
+            info[f"{name}_loss"], info[f"{name}_acc"] = out2[0], out2[1]
+            heads[name] = dict(lse=lse, coeff=coeff, in_loss=(name == "lang_viz" or use_vv), **hd)
+        tot = bf.get("tmp.loss", (1,), torch.float32)
+        ops.axpby(bf.get("tmp.lang_viz.out", (2,), torch.float32)[:1], tot, 1.0, 0.0)
+        if use_vv:
+            ops.axpby(bf.get("tmp.viz_viz.out", (2,), torch.float32)[:1], tot, 1.0, 1.0)
+        info["loss"] = tot[0]
+        loss = bf.get("tmp.loss_scaled", (1,), torch.float32)
+        ops.axpby(tot, loss, coef, 0.0)
+        self._heads["tmp"] = dict(heads=heads, labels=labels, idx_l=idx_l, idx_v=idx_v)
+        return loss[0], info
+
+    def _temporal_bwd(self, d_yj):
+        st, bf = self.store, self._bufs
+        B, n, H = self.B, self.num_chunks_in_group, self.hidden_size
+        t = self._heads["tmp"]
+        _, _, idxA, idxB = self._temporal_index()
+        d_hl = bf.get("tmp.d_hl", (B * n, H), torch.float32, zero=True)
+        d_hv = bf.get("tmp.d_hv", (B * n, H), torch.float32, zero=True)
+        for name, da, db in (("lang_viz", d_hl, d_hv), ("viz_viz", d_hv, d_hv)):
+            hd = t["heads"][name]
+            if not hd["in_loss"]:
+                continue
+            R, scope, tag = hd["R"], hd["scope"], hd["tag"]
+            dlog = bf.get(f"{tag}.dlogits", (R, 8), torch.float32)
+            ops.softmax_ce_bwd(hd["logits"], t["labels"], 4, hd["lse"], hd["coeff"], dlog)
+            d_an = self._dense_bwd(tag, hd["mlp"]["an"], f"{scope}/logits", dlog)
+            d_hj = self._mlp_ln_bwd(hd["mlp"], d_an)  # fp32 [R, 2H]
+            ops.scatter_add_rows(d_hj[:, :H], idxA, da, H=H)
+            ops.scatter_add_rows(d_hj[:, H:], idxB, db, H=H)
+        ops.scatter_add_rows(d_hl, t["idx_l"], d_yj)
+        ops.scatter_add_rows(d_hv, t["idx_v"], d_yj)
+
+    # ---------------------------------------------------------------------------------------------------------
+    # backward of the whole model: call after mask_loss / contrastive_loss / temporal_loss (whichever are in the loss)
+    # ---------------------------------------------------------------------------------------------------------
+    def backward(self):
+        """d(lang_loss + contr_loss + temp_loss)/d(params) accumulated into store.g  (model/modeling.py:713 loss,
+        utils/optimization.py:176 tf.gradients)."""
+        if not self._save:
+            raise RuntimeError("MerlotModel was built without save_for_backward (is_training=False)")
+        cfg, st, bf, D = self.config, self.store, self._bufs, self._dims
+        H, B, Lj, N = self.hidden_size, self.B, self.L, D["N"]
+        Sj, Pz, vcl, Sv, Mv, np_, ncls = D["Sj"], D["Pz"], D["vcl"], D["Sv"], D["Mv"], D["np"], D["ncls"]
+        vt = "vision_backbone/vision_transformer"
+        d_yj = bf.get("bwd.d_yj", (B * Sj, H), torch.bfloat16, zero=True)
+        d_img_trg = bf.get("bwd.d_img_trg", (N, H), torch.float32, zero=True)
+        d_lang_trg = None
+        if self._mask_input:
+            d_lang_trg = bf.get("bwd.d_lang_trg", (self.batch_size * self.num_chunks, H), torch.float32, zero=True)
+        if "mlm" in self._heads:
+            self._mask_loss_bwd(d_yj)
+        if "ctr" in self._heads:
+            self._contrastive_bwd(d_lang_trg, d_img_trg)
+        if "tmp" in self._heads:
+            self._temporal_bwd(d_yj)
+        p_emb = float(self.dropout_prob or 0.0)
+        # ---- joint encoder ----
+        d_jin = bf.get("bwd.d_jin", (B * Sj, H), torch.bfloat16)
+        self._joint.backward(d_yj, d_jin)
+        # lang piece: embed_norm(position_embeddings) -> word / position tables
+        self._embed_bwd("emb_j", "position_embeddings", self._ids_j, d_jin, (Lj, Sj, Pz), (p_emb, self._seed, _SITE_EMB_J), B, Lj)
+        # viz piece: final_ln -> K7 backward
+        dxz = bf.get("bwd.dxsum_z", (B * Pz, H), torch.float32)
+        ops.layernorm_bwd(d_jin, bf.get("viz.xsum", (B * Pz, H), torch.float32), bf.get("viz.mean", (B * Pz,), torch.float32),
+                          bf.get("viz.rstd", (B * Pz,), torch.float32), st.P("vision_backbone/LayerNorm_final_ln/gamma"), dxz,
+                          st.G("vision_backbone/LayerNorm_final_ln/gamma"), st.G("vision_backbone/LayerNorm_final_ln/beta"),
+                          rows=B * Pz, remap=(Pz, Sj, 0))
+        d_hv = bf.get("bwd.d_hv", (Mv, H), torch.bfloat16)
+        ops.viz_assemble_bwd(dxz, d_img_trg, d_hv, N, D["h1"], D["w1"], ncls, D["sp"], H)
+        ops.segment_rowsum_scatter(dxz, N, vcl, self._img_idx, st.G("vision_backbone/img_idx_pe"), H)
+        ops.group_rowsum(dxz, N, vcl, 0, 1, None, st.G("vision_backbone/final_pe/cls_emb"), H)
+        ops.group_rowsum(dxz, N, vcl, 1, D["h2"] * D["w2"], self._grid_idxmap(D["h2"], D["w2"]),
+                         st.G("vision_backbone/final_pe/pos_embs"), H)
+        # ---- ViT ----
+        d_h0v = bf.get("bwd.d_h0v", (Mv, H), torch.bfloat16)
+        self._vit.backward(d_hv, d_h0v)
+        dxv = bf.get("bwd.dxsum_v", (Mv, H), torch.float32)
+        ops.layernorm_bwd(d_h0v, bf.get("vit.xsum", (Mv, H), torch.float32), bf.get("vit.mean0", (Mv,), torch.float32),
+                          bf.get("vit.rstd0", (Mv,), torch.float32), st.P(f"{vt}/LayerNorm_ctx_patches_pre_ln/gamma"), dxv,
+                          st.G(f"{vt}/LayerNorm_ctx_patches_pre_ln/gamma"), st.G(f"{vt}/LayerNorm_ctx_patches_pre_ln/beta"), rows=Mv)
+        ops.group_rowsum(dxv, N, Sv, 0, ncls, None, st.G(f"{vt}/pos_embs/cls_emb"), H)
+        ops.group_rowsum(dxv, N, Sv, ncls, np_, self._grid_idxmap(D["h1"], D["w1"]), st.G(f"{vt}/pos_embs/pos_embs"), H)
+        dpatch = bf.get("bwd.dpatch", (N * np_, H), torch.bfloat16)
+        ops.vit_assemble_bwd(dxv, dpatch, N, np_, ncls, H)
+        ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
+        ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
+                 out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
+        # ---- language-only encoder ----
+        if self._mask_input:
+            Blo, Llo = self._ids_lo.shape
+            d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
+            ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
+            d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
+            self._lo.backward(d_ylo, d_h0lo)
+            self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
+                            Blo, Llo)
+
+    def _embed_bwd(self, tag, norm_scope_name, ids_2d, dy, remap, dropout, groups, Lseq):
+        st, bf = self.store, self._bufs
+        H, R = self.hidden_size, ids_2d.numel()
+        dx = bf.get(f"bwd.dxsum.{tag}", (R, H), torch.float32)
+        ops.layernorm_bwd(dy, bf.get(f"{tag}.xsum", (R, H), torch.float32), bf.get(f"{tag}.mean", (R,), torch.float32),
+                          bf.get(f"{tag}.rstd", (R,), torch.float32), st.P(f"{norm_scope_name}/LayerNorm_embed_norm/gamma"), dx,
+                          st.G(f"{norm_scope_name}/LayerNorm_embed_norm/gamma"), st.G(f"{norm_scope_name}/LayerNorm_embed_norm/beta"),
+                          rows=R, remap=remap, dropout=dropout if self.is_training else (0.0, 0, 0))
+        ops.scatter_add_rows(dx, ids_2d.reshape(-1), st.G("word_embeddings/word_embeddings"))
+        ops.group_rowsum(dx, groups, Lseq, 0, Lseq, None, st.G(f"{norm_scope_name}/position_embeddings"), H)
+
+    def _grid_idxmap(self, nh, nw):
+        key = ("_grid", nh, nw)
+        d = self._bufs.d
+        if key not in d:
+            i = torch.arange(nh, device=self.store.device)[:, None]
+            j = torch.arange(nw, device=self.store.device)[None]
+            d[key] = (i * 64 + j).reshape(-1).to(torch.int32)
+        return d[key]

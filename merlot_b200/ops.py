@@ -140,3 +140,228 @@ def attention_colsum(qkv, lse, colsum, B, S, heads, valid=None):
     a.lse, a.colsum = lse.data_ptr(), colsum.data_ptr()
     L.check(L.lib().merlot_attention_colsum(C.byref(a), _stream()))
     return colsum
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# thin wrappers over the remaining C-ABI entry points (pointer plumbing only)
+# ---------------------------------------------------------------------------------------------------------------
+def _f32(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 1
+    assert t.dtype == torch.bfloat16, t.dtype
+    return 0
+
+
+def layernorm_fwd(x, y, gamma, beta, mean=None, rstd=None, rows=None, remap=(0, 0, 0), dropout=(0.0, 0, 0), eps=1e-5):
+    _require_cuda(x, y, gamma, beta, mean, rstd)
+    d = L.LnDesc()
+    H = gamma.numel()
+    d.x, d.x_f32, d.ld_x = x.data_ptr(), _f32(x), x.stride(-2)
+    d.y, d.y_f32, d.ld_y = y.data_ptr(), _f32(y), y.stride(-2)
+    d.gamma, d.beta = gamma.data_ptr(), beta.data_ptr()
+    d.mean, d.rstd = _ptr(mean), _ptr(rstd)
+    d.rows = x.numel() // H if rows is None else rows
+    d.H, d.eps = H, eps
+    d.map_per, d.map_stride, d.map_off = remap
+    d.dropout_p, d.dropout_seed, d.dropout_site = dropout
+    L.check(L.lib().merlot_layernorm_fwd(C.byref(d), _stream()))
+    return y
+
+
+_ln_ws = {}
+
+
+def _ln_workspace(H: int, device) -> torch.Tensor:
+    key = (H, str(device))
+    if key not in _ln_ws:
+        _ln_ws[key] = torch.empty(L.lib().merlot_layernorm_bwd_workspace_bytes(H), dtype=torch.uint8, device=device)
+    return _ln_ws[key]
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dres=None, rows=None, remap=(0, 0, 0), dropout=(0.0, 0, 0)):
+    _require_cuda(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dres)
+    d = L.LnBwdDesc()
+    H = gamma.numel()
+    d.dy, d.dy_f32, d.ld_dy = dy.data_ptr(), _f32(dy), dy.stride(-2)
+    d.x, d.x_f32, d.ld_x = x.data_ptr(), _f32(x), x.stride(-2)
+    d.mean, d.rstd, d.gamma = mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr()
+    if dres is not None:
+        d.dres, d.ld_dres = dres.data_ptr(), dres.stride(-2)
+    d.dx, d.dx_f32, d.ld_dx = dx.data_ptr(), _f32(dx), dx.stride(-2)
+    d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    d.workspace = _ln_workspace(H, x.device).data_ptr()
+    d.rows = x.numel() // H if rows is None else rows
+    d.H = H
+    d.map_per, d.map_stride, d.map_off = remap
+    d.dropout_p, d.dropout_seed, d.dropout_site = dropout
+    L.check(L.lib().merlot_layernorm_bwd(C.byref(d), _stream()))
+    return dx
+
+
+def bias_grad(dy, out, rows=None, N=None):
+    N = out.numel() if N is None else N
+    rows = dy.numel() // dy.stride(-2) if rows is None else rows
+    L.check(L.lib().merlot_bias_grad(C.c_void_p(dy.data_ptr()), _f32(dy), dy.stride(-2), C.c_longlong(rows), N,
+                                     C.c_void_p(out.data_ptr()), C.c_float(0.0), C.c_uint64(0), C.c_uint32(0), _stream()))
+
+
+def gather_rows(src, idx, dst, n=None, H=None):
+    H = src.shape[-1] if H is None else H
+    n = idx.numel() if n is None else n
+    assert idx.dtype == torch.int32
+    L.check(L.lib().merlot_gather_rows(C.c_void_p(src.data_ptr()), _f32(src), src.stride(-2), C.c_void_p(idx.data_ptr()),
+                                       C.c_void_p(dst.data_ptr()), _f32(dst), dst.stride(-2), n, H, _stream()))
+    return dst
+
+
+def scatter_add_rows(src, idx, dst, n=None, H=None, scale=1.0):
+    H = dst.shape[-1] if H is None else H
+    n = idx.numel() if n is None else n
+    assert idx.dtype == torch.int32
+    L.check(L.lib().merlot_scatter_add_rows(C.c_void_p(src.data_ptr()), _f32(src), src.stride(-2), C.c_void_p(idx.data_ptr()),
+                                            C.c_void_p(dst.data_ptr()), _f32(dst), dst.stride(-2), n, H, C.c_float(scale),
+                                            _stream()))
+    return dst
+
+
+def gelu_f32(x, y):
+    L.check(L.lib().merlot_gelu_f32(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()), _stream()))
+    return y
+
+
+def gelu_bwd_f32(dy, pre, dx):
+    L.check(L.lib().merlot_gelu_bwd_f32(C.c_void_p(dy.data_ptr()), C.c_void_p(pre.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                        C.c_longlong(dy.numel()), _stream()))
+    return dx
+
+
+def cast_f32_to_bf16(x, y):
+    assert x.dtype == torch.float32 and y.dtype == torch.bfloat16 and x.numel() == y.numel()
+    L.check(L.lib().merlot_cast_f32_to_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()), _stream()))
+    return y
+
+
+def cast_bf16_to_f32(x, y):
+    assert x.dtype == torch.bfloat16 and y.dtype == torch.float32 and x.numel() == y.numel() and x.is_contiguous()
+    L.check(L.lib().merlot_cast_bf16_to_f32(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()), _stream()))
+    return y
+
+
+def l2norm_fwd(x, y, inv):
+    L.check(L.lib().merlot_l2norm_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(inv.data_ptr()),
+                                      x.shape[0], x.shape[1], _stream()))
+
+
+def l2norm_bwd(dy, y, inv, dx):
+    L.check(L.lib().merlot_l2norm_bwd(C.c_void_p(dy.data_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(inv.data_ptr()),
+                                      C.c_void_p(dx.data_ptr()), y.shape[0], y.shape[1], _stream()))
+
+
+def softmax_ce_fwd(logits, labels, Cn, loss, lse, correct=None):
+    L.check(L.lib().merlot_softmax_ce_fwd(C.c_void_p(logits.data_ptr()), logits.stride(0), C.c_void_p(labels.data_ptr()),
+                                          logits.shape[0], Cn, C.c_void_p(loss.data_ptr()), C.c_void_p(lse.data_ptr()),
+                                          C.c_void_p(_ptr(correct)), _stream()))
+
+
+def softmax_ce_bwd(logits, labels, Cn, lse, coeff, dlogits):
+    L.check(L.lib().merlot_softmax_ce_bwd(C.c_void_p(logits.data_ptr()), logits.stride(0), C.c_void_p(labels.data_ptr()),
+                                          logits.shape[0], Cn, C.c_void_p(lse.data_ptr()), C.c_void_p(coeff.data_ptr()),
+                                          C.c_void_p(dlogits.data_ptr()), _f32(dlogits), dlogits.stride(0), _stream()))
+
+
+def patch_im2col(image, a, P):
+    N, H0, W0, _ = image.shape
+    assert image.dtype == torch.bfloat16 and image.is_contiguous()
+    L.check(L.lib().merlot_patch_im2col(C.c_void_p(image.data_ptr()), C.c_void_p(a.data_ptr()), N, H0, W0, P, _stream()))
+
+
+def vit_assemble_fwd(patch, pos_table, cls_emb, xsum, N, h1, w1, ncls, H):
+    L.check(L.lib().merlot_vit_assemble_fwd(C.c_void_p(patch.data_ptr()), C.c_void_p(pos_table.data_ptr()),
+                                            C.c_void_p(cls_emb.data_ptr()), C.c_void_p(xsum.data_ptr()), N, h1, w1, ncls, 64, H,
+                                            _stream()))
+
+
+def vit_assemble_bwd(dxsum, dpatch, N, np_, ncls, H):
+    L.check(L.lib().merlot_vit_assemble_bwd(C.c_void_p(dxsum.data_ptr()), C.c_void_p(dpatch.data_ptr()), N, np_, ncls, H, _stream()))
+
+
+def viz_assemble_fwd(hv, img_idx_pe, img_idx, fpos, fcls, xsum, img_trg, N, h1, w1, ncls, sp, H):
+    L.check(L.lib().merlot_viz_assemble_fwd(C.c_void_p(hv.data_ptr()), C.c_void_p(img_idx_pe.data_ptr()),
+                                            C.c_void_p(img_idx.data_ptr()), C.c_void_p(fpos.data_ptr()), C.c_void_p(fcls.data_ptr()),
+                                            C.c_void_p(xsum.data_ptr()), C.c_void_p(img_trg.data_ptr()), N, h1, w1, ncls, sp, 64, H,
+                                            _stream()))
+
+
+def viz_assemble_bwd(dxsum, d_img_trg, dhv, N, h1, w1, ncls, sp, H):
+    L.check(L.lib().merlot_viz_assemble_bwd(C.c_void_p(dxsum.data_ptr()), C.c_void_p(_ptr(d_img_trg)), C.c_void_p(dhv.data_ptr()),
+                                            N, h1, w1, ncls, sp, H, _stream()))
+
+
+def embed_fwd(ids, emb, pos, xsum, Lseq):
+    L.check(L.lib().merlot_embed_fwd(C.c_void_p(ids.data_ptr()), C.c_void_p(emb.data_ptr()), C.c_void_p(pos.data_ptr()),
+                                     C.c_void_p(xsum.data_ptr()), C.c_longlong(ids.numel()), Lseq, emb.shape[1], _stream()))
+
+
+def group_rowsum(src, groups, per, t0, nt, idxmap, dst, H):
+    L.check(L.lib().merlot_group_rowsum(C.c_void_p(src.data_ptr()), src.stride(-2), groups, per, t0, nt, C.c_void_p(_ptr(idxmap)),
+                                        C.c_void_p(dst.data_ptr()), dst.stride(-2), H, _stream()))
+
+
+def segment_rowsum_scatter(src, n_seg, per, idx, dst, H):
+    L.check(L.lib().merlot_segment_rowsum_scatter(C.c_void_p(src.data_ptr()), src.stride(-2), n_seg, per, C.c_void_p(idx.data_ptr()),
+                                                  C.c_void_p(dst.data_ptr()), dst.stride(-2), H, _stream()))
+
+
+def ids_valid(ids, valid):
+    L.check(L.lib().merlot_ids_valid(C.c_void_p(ids.data_ptr()), C.c_void_p(valid.data_ptr()), C.c_longlong(ids.numel()), _stream()))
+
+
+def joint_valid(ids, valid, B, P, Lseq):
+    L.check(L.lib().merlot_joint_valid(C.c_void_p(ids.data_ptr()), C.c_void_p(valid.data_ptr()), B, P, Lseq, _stream()))
+
+
+def mlm_index(ids, masked_idx, rows, targets, B, Lseq, k, P):
+    L.check(L.lib().merlot_mlm_index(C.c_void_p(ids.data_ptr()), C.c_void_p(masked_idx.data_ptr()), C.c_void_p(rows.data_ptr()),
+                                     C.c_void_p(targets.data_ptr()), B, Lseq, k, P, _stream()))
+
+
+def temporal_labels(video_src_ids, shuffled_idx, labels, weights, B, n):
+    L.check(L.lib().merlot_temporal_labels(C.c_void_p(video_src_ids.data_ptr()), C.c_void_p(shuffled_idx.data_ptr()),
+                                           C.c_void_p(labels.data_ptr()), C.c_void_p(weights.data_ptr()), B, n, _stream()))
+
+
+def weighted_loss(per_row, correct, weights, nz_labels, denom_mode, scale, out2, coeff):
+    L.check(L.lib().merlot_weighted_loss(C.c_void_p(per_row.data_ptr()), C.c_void_p(_ptr(correct)), C.c_void_p(_ptr(weights)),
+                                         C.c_void_p(_ptr(nz_labels)), per_row.numel(), denom_mode, C.c_float(scale),
+                                         C.c_void_p(out2.data_ptr()), C.c_void_p(_ptr(coeff)), _stream()))
+
+
+def small_gemm(A, sam, sak, B, sbn, sbk, Cm, M, N, K, alpha=1.0, beta=0.0):
+    L.check(L.lib().merlot_small_gemm_f32(C.c_void_p(A.data_ptr()), C.c_longlong(sam), C.c_longlong(sak), C.c_void_p(B.data_ptr()),
+                                          C.c_longlong(sbn), C.c_longlong(sbk), C.c_void_p(Cm.data_ptr()), Cm.stride(0), M, N, K,
+                                          C.c_float(alpha), C.c_float(beta), _stream()))
+
+
+def axpby(x, y, a=1.0, b=1.0):
+    L.check(L.lib().merlot_axpby_f32(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()), C.c_float(a),
+                                     C.c_float(b), _stream()))
+
+
+def mask_inputs(ids, attn_summ, draws, masked_ids, masked_idx, valid_out, num_topk, num_to_mask, do_spanbert, mask_token, consts):
+    m = L.MaskDesc()
+    B, Lseq = ids.shape
+    m.ids, m.attn_summ, m.gumbel = ids.data_ptr(), _ptr(attn_summ), draws["gumbel"].data_ptr()
+    m.span_lower, m.span_upper = _ptr(draws.get("span_lower")), _ptr(draws.get("span_upper"))
+    m.option, m.rand_ids = draws["option"].data_ptr(), draws["rand_ids"].data_ptr()
+    m.masked_ids, m.masked_idx, m.valid_out = masked_ids.data_ptr(), masked_idx.data_ptr(), _ptr(valid_out)
+    m.B, m.L, m.num_topk, m.num_to_mask, m.do_spanbert, m.mask_token = B, Lseq, num_topk, num_to_mask, int(do_spanbert), mask_token
+    m.w_delta, m.w_non, m.logw_top, m.logw_non, m.w_max = consts
+    L.check(L.lib().merlot_mask_inputs(C.byref(m), _stream()))
+
+
+def adamw_step(p, g, m, v, p_bf16, n, beta1, omb1, beta2, omb2, eps, lr_t, wd, grad_scale, zero_grad):
+    d = L.AdamDesc()
+    d.p, d.g, d.m, d.v, d.p_bf16, d.n = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p_bf16), n
+    d.beta1, d.one_minus_beta1, d.beta2, d.one_minus_beta2 = beta1, omb1, beta2, omb2
+    d.epsilon, d.lr_t, d.weight_decay, d.grad_scale, d.zero_grad = eps, lr_t, wd, grad_scale, int(zero_grad)
+    L.check(L.lib().merlot_adamw_step(C.byref(d), _stream()))

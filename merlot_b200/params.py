@@ -1,0 +1,253 @@
+"""Parameter arena: every trainable variable of the reference in ONE flat fp32 master buffer, with
+matching flat buffers for the fp32 gradients (the NCCL all-reduce bucket), the bf16 Adam first moment, the sign-packed
+bf16 second moment (utils/optimization.py:371-383) and the bf16 compute copy (bfloat16_getter,
+utils/model_utils.py:572-602).  Layout in HBM: [hyper-parameter group 0 | group 1 | ...], each variable padded to 64
+elements so every slice is 256-byte (fp32) / 128-byte (bf16) aligned and usable as a TMA base.
+
+Storage differs from the TF variables in three places (converted by load_tf_dict / to_tf_dict):
+  * query/key/value kernels [H,H] x3 are fused into `.../qkv/kernel` [H,3H] (and biases into [3H]);
+  * the temporal `logits` layer [H,4] is zero-padded to [H,8] so its rows are 16-byte aligned for TMA;
+  * the patch conv kernel [P,P,3,H] is stored as the im2col matrix [P*P*3, H] (same memory order).
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+PAD = 64
+TEMPORAL_PAD_N = 8
+
+
+@dataclass
+class Entry:
+    name: str
+    shape: Tuple[int, ...]
+    tf_names: Tuple[str, ...]   # reference variable name(s) this entry stores
+    offset: int = 0
+    numel: int = 0
+    padded: int = 0
+    hyper: Tuple = ()
+
+
+def _entries(cfg: dict) -> List[Entry]:
+    H, I, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
+    P = cfg["patch_size"]
+    out: List[Entry] = []
+
+    def add(name, shape, tf_names=None):
+        out.append(Entry(name, tuple(shape), tuple(tf_names) if tf_names else (name,)))
+
+    def ln(scope):
+        add(f"{scope}/gamma", (H,))
+        add(f"{scope}/beta", (H,))
+
+    def lin(scope, i, o):
+        add(f"{scope}/kernel", (i, o))
+        add(f"{scope}/bias", (o,))
+
+    def stack(scope, n):
+        for l in range(n):
+            ls = f"{scope}/layer{l:02d}"
+            ln(f"{ls}/LayerNorm_attn_ln0")
+            add(f"{ls}/qkv/kernel", (H, 3 * H), [f"{ls}/{x}/kernel" for x in ("query_layer", "key_layer", "value_layer")])
+            add(f"{ls}/qkv/bias", (3 * H,), [f"{ls}/{x}/bias" for x in ("query_layer", "key_layer", "value_layer")])
+            lin(f"{ls}/context_projection_layer", H, H)
+            ln(f"{ls}/LayerNorm_mlp_ln0")
+            lin(f"{ls}/intermediate", H, I)
+            lin(f"{ls}/output", I, H)
+        ln(f"{scope}/LayerNorm_ln_final")
+
+    vt = "vision_backbone/vision_transformer"
+    add(f"{vt}/conv2d/kernel", (P * P * 3, H))
+    add(f"{vt}/conv2d/bias", (H,))
+    add(f"{vt}/pos_embs/pos_embs", (64 * 64, H))
+    add(f"{vt}/pos_embs/cls_emb", (cfg.get("num_cls_emb", 2), H))
+    ln(f"{vt}/LayerNorm_ctx_patches_pre_ln")
+    stack(vt, cfg.get("num_vision_transformer_hidden_layers", cfg["num_hidden_layers"]))
+    add("vision_backbone/img_idx_pe", (cfg.get("max_vision_pos_embeddings", 1024), H))
+    add("vision_backbone/final_pe/pos_embs", (64 * 64, H))
+    add("vision_backbone/final_pe/cls_emb", (1, H))
+    ln("vision_backbone/LayerNorm_final_ln")
+    add("word_embeddings/word_embeddings", (V, H))
+    for sc in ("position_embeddings", "langonly_embeddings"):
+        add(f"{sc}/position_embeddings", (cfg["max_position_embeddings"], H))
+        ln(f"{sc}/LayerNorm_embed_norm")
+    stack("encoder", max(cfg["num_hidden_layers"], cfg.get("num_lang_transformer_hidden_layers", 0)))
+    if cfg.get("do_projection", False):
+        lin("lm_head/projection", H, H)
+        ln("lm_head/LayerNorm")
+    if cfg.get("do_bias", False):
+        add("lm_head/output_bias", (V,))
+    Cs = cfg.get("contrastive_size", H)
+    for t in ("lang", "viz"):
+        if cfg.get("do_projection", False):
+            lin(f"contrastive/{t}_proj_intermediate", H, Cs)
+            add(f"contrastive/LayerNorm_{t}_proj_ln/gamma", (Cs,))
+            add(f"contrastive/LayerNorm_{t}_proj_ln/beta", (Cs,))
+        lin(f"contrastive/{t}_proj", Cs if cfg.get("do_projection", False) else H, Cs)
+    for t in ("lang_viz", "viz_viz"):
+        lin(f"{t}_temporal/intermediate", 2 * H, H)
+        ln(f"{t}_temporal/LayerNorm_ln0")
+        add(f"{t}_temporal/logits/kernel", (H, TEMPORAL_PAD_N))
+        add(f"{t}_temporal/logits/bias", (TEMPORAL_PAD_N,))
+    return out
+
+
+def hyper_for(tf_name: str, optimizer_cfg: dict) -> Tuple[float, float, float, float, float]:
+    """(learning_rate, weight_decay_rate, beta_1, beta_2, epsilon) after the regex overrides of
+    utils/optimization.py:125-147 (re.search on the variable name; later rules update earlier ones)."""
+    hp = {
+        "learning_rate": optimizer_cfg["learning_rate"],
+        "weight_decay_rate": optimizer_cfg.get("weight_decay_rate", 1e-4),
+        "beta_1": 0.9,  # hard-coded, optimization.py:185
+        "beta_2": optimizer_cfg.get("beta_2", 0.98),
+        "epsilon": optimizer_cfg.get("epsilon", 1e-6),
+    }
+    overrides = list(optimizer_cfg.get("param_overrides", None) or [])
+    if optimizer_cfg.get("freeze_scope") is not None:  # :128-131
+        overrides.append([[f"^{optimizer_cfg['freeze_scope']}"], {"learning_rate": 0}])
+    for regexes, over in overrides:
+        for k in over:
+            if k not in ("learning_rate", "weight_decay_rate", "beta_1", "beta_2", "epsilon", "do_factor"):
+                raise ValueError("Regex rule {} -> {} isn't OK because {} isn't a changable optimization parameter".format(
+                    regexes, over, k))
+        for regex in regexes:
+            if re.search(regex, tf_name) is not None:
+                hp.update({k: v for k, v in over.items() if k in hp})
+    return (hp["learning_rate"], hp["weight_decay_rate"], hp["beta_1"], hp["beta_2"], hp["epsilon"])
+
+
+class ParamStore:
+    """Flat arenas + named views.  `optimizer_cfg` fixes the hyper-parameter grouping (needed only for training)."""
+
+    def __init__(self, model_cfg: dict, device="cuda", optimizer_cfg: Optional[dict] = None, with_optimizer_state=True):
+        if len(model_cfg.get("resnet_layers", []) or []) != 0:
+            raise NotImplementedError(
+                "resnet_layers={} selects the hybrid ResNet-lite stem (utils/vision_transformer.py:206-223), which this "
+                "build does not provide yet; use config.patch_embed_variant() for the 16x16 patch-embed ViT".format(
+                    model_cfg.get("resnet_layers")))
+        self.cfg = model_cfg
+        self.device = torch.device(device)
+        ents = _entries(model_cfg)
+        ocfg = optimizer_cfg or {"learning_rate": 0.0, "param_overrides": [
+            [["LayerNorm", "layer_norm", "GroupNorm", "bias"], {"weight_decay_rate": 0}]]}
+        for e in ents:
+            hs = {hyper_for(t, ocfg) for t in e.tf_names}
+            if len(hs) != 1:
+                raise NotImplementedError(f"param_overrides treat the fused tensors {e.tf_names} differently")
+            e.hyper = hs.pop()
+            e.numel = math.prod(e.shape)
+            e.padded = (e.numel + PAD - 1) // PAD * PAD
+        groups: Dict[Tuple, List[Entry]] = {}
+        for e in ents:
+            groups.setdefault(e.hyper, []).append(e)
+        self.entries: Dict[str, Entry] = {}
+        self.groups: List[Tuple[Tuple, int, int]] = []  # (hyper, offset, count)
+        off = 0
+        for hyper, es in sorted(groups.items(), key=lambda kv: -kv[0][1]):
+            start = off
+            for e in es:
+                e.offset = off
+                off += e.padded
+                self.entries[e.name] = e
+            self.groups.append((hyper, start, off - start))
+        self.total = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.pb = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
+        if with_optimizer_state:
+            self.m = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
+            self.v = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
+        self.global_step = 0
+
+    # ---- views ----
+    def _view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        e = self.entries[name]
+        return buf[e.offset:e.offset + e.numel].view(e.shape)
+
+    def P(self, name):
+        return self._view(self.p, name)
+
+    def G(self, name):
+        return self._view(self.g, name)
+
+    def W(self, name):  # bf16 compute copy
+        return self._view(self.pb, name)
+
+    def num_params(self) -> int:
+        """Trainable scalars as the reference counts them (padding and the 4 dead logits columns excluded)."""
+        n = 0
+        for e in self.entries.values():
+            n += e.numel if "temporal/logits" not in e.name else e.numel // 2
+        return n
+
+    def sync_bf16(self):
+        """bf16 compute copy <- fp32 master (one pass; afterwards the fused AdamW keeps it current)."""
+        if self.device.type != "cuda":
+            self.pb.copy_(self.p.to(torch.bfloat16))
+        else:
+            ops.cast_f32_to_bf16(self.p, self.pb)
+
+    # ---- interop with the reference's variable names ----
+    def load_tf_dict(self, d: Dict[str, torch.Tensor]):
+        with torch.no_grad():
+            for e in self.entries.values():
+                dst = self.P(e.name)
+                if len(e.tf_names) == 3:
+                    src = torch.cat([d[t] for t in e.tf_names], dim=-1)
+                elif "temporal/logits" in e.name:
+                    src = torch.zeros(e.shape, dtype=torch.float32)
+                    src[..., :4] = d[e.tf_names[0]]
+                else:
+                    src = d[e.tf_names[0]].reshape(e.shape)
+                dst.copy_(src.to(torch.float32))
+        self.sync_bf16()
+
+    def to_tf_dict(self, which: str = "p") -> Dict[str, torch.Tensor]:
+        buf = {"p": self.p, "g": self.g}[which]
+        out = {}
+        for e in self.entries.values():
+            t = self._view(buf, e.name).detach().float().cpu()
+            if len(e.tf_names) == 3:
+                for nm, part in zip(e.tf_names, t.chunk(3, dim=-1)):
+                    out[nm] = part.contiguous()
+            elif "temporal/logits" in e.name:
+                out[e.tf_names[0]] = t[..., :4].contiguous()
+            elif e.name.endswith("conv2d/kernel"):
+                Pp = self.cfg["patch_size"]
+                out[e.tf_names[0]] = t.reshape(Pp, Pp, 3, -1)
+            elif e.name.endswith("pos_embs/pos_embs"):
+                out[e.tf_names[0]] = t.reshape(1, 64, 64, -1)
+            elif e.name.endswith("/cls_emb"):
+                out[e.tf_names[0]] = t.reshape(1, t.shape[0], -1)
+            else:
+                out[e.tf_names[0]] = t
+        return out
+
+    def init_reference(self, seed: int = 0):
+        """Reference initialisers (truncated normal 0.02 / variance-scaling patch kernel / LN 1,0 / zero biases)."""
+        g = torch.Generator().manual_seed(seed)
+        std = self.cfg.get("initializer_range", 0.02)
+        with torch.no_grad():
+            for e in self.entries.values():
+                leaf = e.name.rsplit("/", 1)[-1]
+                if leaf == "gamma":
+                    t = torch.ones(e.shape)
+                elif leaf in ("beta", "bias", "output_bias"):
+                    t = torch.zeros(e.shape)
+                else:
+                    s_ = std
+                    if e.name.endswith("conv2d/kernel"):
+                        s_ = math.sqrt(1.0 / e.shape[0]) / 0.87962566103423978
+                    t = torch.empty(e.shape)
+                    torch.nn.init.trunc_normal_(t, 0.0, s_, -2 * s_, 2 * s_, generator=g)
+                    if "temporal/logits/kernel" in e.name:
+                        t[:, 4:] = 0
+                self.P(e.name).copy_(t)
+        self.sync_bf16()
