@@ -222,7 +222,7 @@ class ParamStore:
             elif e.name.endswith("conv2d/kernel"):
                 Pp = self.cfg["patch_size"]
                 out[e.tf_names[0]] = t.reshape(Pp, Pp, 3, -1)
-            elif e.name.endswith("pos_embs/pos_embs"):
+            elif e.name.endswith("/pos_embs"):
                 out[e.tf_names[0]] = t.reshape(1, 64, 64, -1)
             elif e.name.endswith("/cls_emb"):
                 out[e.tf_names[0]] = t.reshape(1, t.shape[0], -1)
