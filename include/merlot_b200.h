@@ -278,6 +278,11 @@ int merlot_small_gemm_f32(const float* A, long long sam, long long sak, const fl
                           int ldc, int M, int N, int K, float alpha, float beta, void* stream);
 int merlot_axpby_f32(const float* x, float* y, long long n, float a, float b, void* stream);
 
+/* bench.py roofline support: time every K1 launch with CUDA events on its own stream between begin/end.
+ * end() synchronises the device and returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count. */
+void merlot_gemm_profile_begin(void);
+int merlot_gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,8 @@
 #include "host_common.h"
 #include "ptx.cuh"
 
+#include <vector>
+
 namespace mb {
 
 constexpr int BLOCK_M = 128;
@@ -306,6 +308,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 }
 
+// Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every GEMM launch.
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
                             cudaStream_t stream) {
@@ -316,8 +323,19 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
+  ProfRec rec;
+  if (g_prof_on) {
+    MB_CHECK_CUDA(cudaEventCreate(&rec.e0));
+    MB_CHECK_CUDA(cudaEventCreate(&rec.e1));
+    rec.flops = 2.0 * (double)p.M * (double)p.N * (double)p.K;
+    MB_CHECK_CUDA(cudaEventRecord(rec.e0, stream));
+  }
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, p);
   MB_CHECK_LAUNCH();
+  if (g_prof_on) {
+    MB_CHECK_CUDA(cudaEventRecord(rec.e1, stream));
+    g_prof.push_back(rec);
+  }
   return MERLOT_OK;
 }
 
@@ -427,4 +445,27 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   if (bn == 256) { MB_GEMM_DISPATCH(256) }
   MB_GEMM_DISPATCH(128)
 #undef MB_GEMM_DISPATCH
+}
+
+extern "C" void merlot_gemm_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+
+extern "C" int merlot_gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  g_prof_on = false;
+  MB_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0, fl = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    MB_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t; fl += r.flops;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (long long)g_prof.size();
+  g_prof.clear();
+  return MERLOT_OK;
 }
