@@ -25,6 +25,13 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+T00 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T00:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 METRIC = "frame-caption segments/sec (fwd+bwd+AdamW)"
 UNIT = "segments/s"
 PER_GPU_BATCH = 8
@@ -89,10 +96,38 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process can really use: CPU affinity, capped by a cgroup CPU quota if one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
+def cpu_threads():
+    # The oracle is ~2000 small-to-medium torch ops per step; beyond ~32 OpenMP threads the per-op fork/join cost on a
+    # shared 128-thread host outweighs the extra cores (measured: >100 s/step with 128 threads vs ~5 s with 8).
+    return int(os.environ.get("MERLOT_CPU_THREADS", min(usable_cores(), 32)))
+
+
 def cpu_reference_step_fn(config, batch):
     """One fwd + bwd + AdamW step of the restated reference math (oracle) on the host cores. Returns (fn, segments)."""
     from oracle import merlot_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     cfg = dict(config.model)
     params = O.init_params(cfg, seed=0)
     leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
@@ -134,7 +169,7 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = segs * args.steps / dt
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -164,8 +199,10 @@ def run_ours(args):
     dist = DataParallel("nccl") if world > 1 else None
     lib = L.lib()
     config = load_config()
+    log("building parameter store")
     model_fn = model_fn_builder(config, dist=dist, device=dev)
     store = model_fn.store
+    log(f"store ready: {store.num_params() / 1e6:.1f} M params")
     segs_per_rank = PER_GPU_BATCH * config.model["num_chunks_in_group"]
 
     def sync_all():
@@ -181,8 +218,10 @@ def run_ours(args):
         spec.train_op()
         return spec
 
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         one_step(feats)
+        torch.cuda.synchronize()
+        log(f"warmup step {i} done")
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     lib.merlot_reset_launch_count()
@@ -193,6 +232,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     launches = int(lib.merlot_launch_count())
+    log("timed region done")
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist is not None:
         dist.dist.all_reduce(ms, op=dist.dist.ReduceOp.MAX)
@@ -217,6 +257,7 @@ def run_ours(args):
     if dist is not None:
         dist.dist.all_reduce(ms_e, op=dist.dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
+    log("e2e region done")
 
     # ---- roofline of the dominant kernel (K1 GEMM), one extra step with per-launch CUDA events ----
     roof = None
@@ -236,17 +277,15 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            step, segs = cpu_reference_step_fn(config, batch=1)
-            step()
-            c0 = time.perf_counter()
-            nrep = 0
-            while nrep < 2 or (time.perf_counter() - c0 < 12 and nrep < 6):
-                step()
-                nrep += 1
-            cdt = time.perf_counter() - c0
-            cpu = {"value": segs * nrep / cdt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"{nrep} steps of batch=1 (4 segments) fwd+bwd+AdamW of the restated reference math (torch fp32; "
-                             "TF 1.15 not installable)"}
+            log("cpu baseline: running `bench.py --impl reference` as a bounded subprocess")
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                                   capture_output=True, text=True, timeout=240)
+                ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                cpu = ref["cpu_baseline"]
+            except Exception as e:  # the baseline is reported, never fatal
+                cpu = {"value": None, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": f"failed/timeout: {e!r}"[:200]}
+            log("cpu baseline done")
         val = segs_per_rank * world * args.steps / (ms_total * 1e-3)
         e2e_val = segs_per_rank * world * args.steps / (float(ms_e) * 1e-3)
         line = {

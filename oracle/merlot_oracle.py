@@ -85,6 +85,17 @@ def position_embedder2d(p: Params, scope: str, num_h: int, num_w: int, num_cls_e
 # ------------------------------------------------------------------------------------------------------------
 # transformer (utils/transformer.py)
 # ------------------------------------------------------------------------------------------------------------
+def attention_core(q, k, v, mask):
+    """utils/transformer.py:98-120 on [B,h,S,d] tensors; mask [B,S,S] in {0,1} or None. Returns (probs, probs @ v)."""
+    d = q.shape[-1]
+    scores = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(float(d)))  # :98-100
+    if mask is not None:
+        m = mask[:, None]
+        scores = scores * m - 1e10 * (1 - m)  # :109-110 (masked entries become exactly -1e10)
+    probs = torch.softmax(scores, dim=-1)  # :112
+    return probs, probs @ v  # :120
+
+
 def attention_layer(x_flat, mask, batch, seq, heads, p: Params, scope: str):
     """utils/transformer.py:33-138 (no cache, attention dropout 0).  mask [B,S,S] in {0,1}.
     Returns (projected context [B*S,H], probs [B,h,S,S])."""
@@ -96,11 +107,8 @@ def attention_layer(x_flat, mask, batch, seq, heads, p: Params, scope: str):
         return y.reshape(batch, seq, heads, d).permute(0, 2, 1, 3)
 
     q, k, v = proj("query_layer"), proj("key_layer"), proj("value_layer")
-    scores = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(float(d)))  # :98-100
-    m = mask[:, None]
-    scores = scores * m - 1e10 * (1 - m)  # :109-110 (masked entries become exactly -1e10)
-    probs = torch.softmax(scores, dim=-1)  # :112
-    ctx = (probs @ v).permute(0, 2, 1, 3).reshape(batch * seq, H)  # :120-127
+    probs, ctx4 = attention_core(q, k, v, mask)
+    ctx = ctx4.permute(0, 2, 1, 3).reshape(batch * seq, H)  # :123-127
     out = dense(ctx, p, f"{scope}/context_projection_layer")  # :130-135
     return out, probs
 

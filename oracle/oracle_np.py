@@ -1,0 +1,70 @@
+"""ORACLE (second, independent restatement) -- TEST INFRASTRUCTURE ONLY.  NumPy fp64 versions of the hot-path primitives,
+written separately from oracle/merlot_oracle.py so the two can check each other (SURVEY.md 8(c) "oracle cross-check").
+PARITY UNPINNED against the reference itself (no reference tests/fixtures exist; TF 1.15 cannot run here).
+Citations relative to /root/reference."""
+import math
+
+import numpy as np
+
+
+def erf(x):
+    """High-precision erf via math.erf (vectorised)."""
+    return np.vectorize(math.erf)(x)
+
+
+def gelu(x):  # utils/model_utils.py:96-110
+    return x * 0.5 * (1.0 + erf(x / math.sqrt(2.0)))
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):  # utils/model_utils.py:113-130
+    mean = x.mean(-1, keepdims=True)
+    var = x.var(-1, keepdims=True)  # biased
+    s = gamma / np.sqrt(var + eps)
+    return x * s - mean * s + beta
+
+
+def softmax(x):
+    e = np.exp(x - x.max(-1, keepdims=True))
+    return e / e.sum(-1, keepdims=True)
+
+
+def attention(x, wq, bq, wk, bk, wv, bv, wo, bo, mask, heads):  # utils/transformer.py:33-138
+    B, S, H = x.shape
+    d = H // heads
+    xf = x.reshape(B * S, H)
+
+    def proj(w, b):
+        return (xf @ w + b).reshape(B, S, heads, d).transpose(0, 2, 1, 3)
+
+    q, k, v = proj(wq, bq), proj(wk, bk), proj(wv, bv)
+    s = q @ k.transpose(0, 1, 3, 2) / math.sqrt(d)
+    m = mask[:, None]
+    s = s * m - 1e10 * (1 - m)
+    p = softmax(s)
+    ctx = (p @ v).transpose(0, 2, 1, 3).reshape(B * S, H)
+    return (ctx @ wo + bo).reshape(B, S, H), p
+
+
+def cross_entropy(logits, labels):  # utils/model_utils.py:313-332
+    z = logits - logits.max(-1, keepdims=True)
+    logp = z - np.log(np.exp(z).sum(-1, keepdims=True))
+    return -np.take_along_axis(logp, labels[..., None], -1)[..., 0]
+
+
+def bf16_round(x):
+    """float32 -> nearest-even bfloat16 -> float32, bit-level."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def decode_v(v_bf16_as_f32):  # utils/optimization.py:268-281
+    a = np.abs(v_bf16_as_f32).astype(np.float32)
+    return np.where(np.sign(v_bf16_as_f32) > 0, a, a * np.float32(1.00390625)).astype(np.float32)
+
+
+def encode_v(v):  # utils/optimization.py:283-288
+    e = bf16_round(v)
+    err0 = np.abs(e - v)
+    err1 = np.abs(e * np.float32(1.00390625) - v)
+    return np.where(err0 <= err1, e, -e).astype(np.float32)

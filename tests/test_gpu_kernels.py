@@ -1,0 +1,239 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu): every CUDA kernel family against the oracle on the same
+seeded inputs, through the C-ABI.  Tolerances: bit-exact for integer/index work and the packed bf16 Adam moments;
+bf16 tensor-core outputs compared in relative Frobenius norm against the fp32 oracle evaluated on the SAME bf16-rounded
+inputs (GEMM fp32-out 1e-4; bf16-out / attention 1e-2 -- one bf16 rounding is 2^-9 = 2e-3 per element)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import merlot_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from merlot_b200 import ops as o
+    return o
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K1 GEMM: all operand-major modes, ragged shapes (every Appendix-B family incl. N = 50370 and M = 200)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (200, 264, 136, 0), (1024, 2304, 768, 0), (3168, 768, 3072, 128),
+                                      (8, 8, 8, 0), (130, 50376, 768, 0)])
+def test_gemm_modes(ops, a_mn, b_mn, M, N, K, bn):
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operands need 16-byte aligned rows")
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.5).bfloat16()
+    b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.5).bfloat16()
+    out = ops.gemm(a.to(DEV), b.to(DEV), a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32, block_n=bn)
+    A = a.float().t() if a_mn else a.float()
+    Bm = b.float() if b_mn else b.float().t()
+    assert rel(out, A @ Bm) < 1e-4
+
+
+def test_gemm_epilogues(ops):
+    g = torch.Generator().manual_seed(1)
+    M, N, K = 520, 768, 768
+    a = (torch.randn(M, K, generator=g) * 0.3).bfloat16()
+    w = (torch.randn(K, N, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g).bfloat16()
+    p = {"d/kernel": w.float(), "d/bias": bias}
+    base = O.dense(a.float(), p, "d")  # tf.layers.dense restatement
+    ad, wd, bd, rd = a.to(DEV), w.to(DEV), bias.to(DEV), resid.to(DEV)
+    assert rel(ops.gemm(ad, wd, b_mn_major=True, bias=bd), base) < 6e-3
+    assert rel(ops.gemm(ad, wd, b_mn_major=True, bias=bd, resid=rd), base + resid.float()) < 6e-3
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    act = ops.gemm(ad, wd, b_mn_major=True, bias=bd, gelu=True, out_pre=pre)
+    assert rel(pre, base) < 6e-3 and rel(act, O.gelu(base)) < 6e-3
+    aux = torch.randn(M, N, generator=g).bfloat16()
+    x = aux.float().requires_grad_(True)
+    O.gelu(x).sum().backward()
+    assert rel(ops.gemm(ad, wd, b_mn_major=True, dgelu_aux=aux.to(DEV)), (a.float() @ w.float()) * x.grad) < 6e-3
+    dy = (torch.randn(M, N, generator=g) * 0.1).bfloat16()
+    dw = torch.zeros(K, N, dtype=torch.float32, device=DEV)
+    for _ in range(2):  # accumulation semantics of the flat gradient arena (shared `encoder` weights get two passes)
+        ops.gemm(ad, dy.to(DEV), a_mn_major=True, b_mn_major=True, out=dw, atomic=True, M=K, N=N, K=M)
+    assert rel(dw, 2 * (a.float().t() @ dy.float())) < 1e-4
+    o1 = ops.gemm(ad, wd, b_mn_major=True, bias=bd, dropout_p=0.1, dropout_seed=7, dropout_site=3)
+    o2 = ops.gemm(ad, wd, b_mn_major=True, bias=bd, dropout_p=0.1, dropout_seed=7, dropout_site=3)
+    o3 = ops.gemm(ad, wd, b_mn_major=True, bias=bd, dropout_p=0.1, dropout_seed=8, dropout_site=3)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    assert abs((o1 == 0).float().mean().item() - 0.1) < 0.01
+    kept = (o1 != 0).cpu()
+    assert rel(o1.cpu()[kept], (base / 0.9)[kept]) < 6e-3  # inverted dropout scaling (tf.nn.dropout)
+
+
+def test_gemm_shape_errors(ops):
+    from merlot_b200._lib import MerlotShapeError
+    a = torch.zeros(16, 12, dtype=torch.bfloat16, device=DEV)  # lda = 12 not a multiple of 8
+    b = torch.zeros(16, 12, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(MerlotShapeError):
+        ops.gemm(a, b)
+    assert issubclass(MerlotShapeError, ValueError)  # the reference raises ValueError on shape mismatches
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K2/K3/K4 attention
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,S,heads,masked", [(1, 128, 1, False), (2, 64, 2, True), (2, 266, 12, False), (2, 396, 12, True),
+                                              (3, 93, 4, True), (1, 885, 2, True), (1, 1, 1, False)])
+def test_attention_fwd_bwd_colsum(ops, B, S, heads, masked):
+    g = torch.Generator().manual_seed(S)
+    H = heads * 64
+    qkv = torch.randn(B * S, 3 * H, generator=g).bfloat16()
+    valid = None
+    mask = None
+    if masked:
+        lens = torch.randint(max(1, S // 3), S + 1, (B,), generator=g)
+        v2 = (torch.arange(S)[None] < lens[:, None])
+        if S > 10:
+            v2[-1, 5:9] = False
+        valid = v2.to(torch.uint8).reshape(-1).contiguous()
+        vf = v2.float()
+        mask = vf[:, None, :] * vf[:, :, None]
+    x = qkv.float().reshape(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = (x[i].clone().requires_grad_(True) for i in range(3))
+    probs, ctx4 = O.attention_core(q, k, v, mask)
+    ctx_ref = ctx4.permute(0, 2, 1, 3).reshape(B * S, H)
+    vd = valid.to(DEV) if valid is not None else None
+    ctx, lse = ops.attention_fwd(qkv.to(DEV), B, S, heads, vd)
+    assert rel(ctx, ctx_ref) < 1e-2
+    d_ctx = (torch.randn(B * S, H, generator=g) * 0.1).bfloat16()
+    if valid is not None:
+        d_ctx = d_ctx * valid[:, None].to(d_ctx.dtype)  # padding rows never receive gradient in the model
+    dqkv = ops.attention_bwd(qkv.to(DEV), ctx, d_ctx.to(DEV), lse, B, S, heads, vd)
+    ctx_ref.backward(d_ctx.float())
+    ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+    for i in range(3):
+        assert rel(dqkv[:, i * H:(i + 1) * H], ref[:, i * H:(i + 1) * H]) < 1.5e-2
+    colsum = torch.zeros(B, S, device=DEV)
+    ops.attention_colsum(qkv.to(DEV), lse, colsum, B, S, heads, vd)
+    assert rel(colsum, probs.detach().mean(1).sum(1)) < 2e-3  # head-mean, summed over queries (transformer.py:208-209)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K5 LayerNorm, CE, l2norm
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,H", [(1, 768), (1000, 768), (37, 128), (8512, 768)])
+def test_layernorm_fwd_bwd(ops, rows, H):
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, H, generator=g) * 2 + 0.5).bfloat16()
+    gam, bet = torch.randn(H, generator=g), torch.randn(H, generator=g)
+    xr = x.float().requires_grad_(True)
+    gr, br = gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    y_ref = O.layer_norm(xr, {"l/gamma": gr, "l/beta": br}, "l")
+    y = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    ops.layernorm_fwd(x.to(DEV), y, gam.to(DEV), bet.to(DEV), mean, rstd)
+    assert rel(y, y_ref) < 4e-3
+    dy = torch.randn(rows, H, generator=g).bfloat16()
+    dres = torch.randn(rows, H, generator=g).bfloat16()
+    y_ref.backward(dy.float())
+    dx = torch.empty(rows, H, dtype=torch.bfloat16, device=DEV)
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    ops.layernorm_bwd(dy.to(DEV), x.to(DEV), mean, rstd, gam.to(DEV), dx, dg, db, dres=dres.to(DEV))
+    assert rel(dx, xr.grad + dres.float()) < 6e-3
+    assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
+
+
+def test_softmax_ce_and_l2norm(ops):
+    g = torch.Generator().manual_seed(0)
+    R, Cn, ld = 37, 50370, 50432
+    logits = torch.zeros(R, ld)
+    logits[:, :Cn] = torch.randn(R, Cn, generator=g) * 3
+    labels = torch.randint(0, Cn, (R,), generator=g, dtype=torch.int32)
+    lr = logits[:, :Cn].clone().requires_grad_(True)
+    per_ref = O.raw_cross_entropy_with_logits(lr, labels)
+    per, lse, corr = (torch.empty(R, device=DEV) for _ in range(3))
+    ops.softmax_ce_fwd(logits.to(DEV), labels.to(DEV), Cn, per, lse, corr)
+    assert torch.allclose(per.cpu(), per_ref.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(corr.cpu(), (lr.argmax(-1) == labels).float())
+    coeff = torch.rand(R, generator=g)
+    (per_ref * coeff).sum().backward()
+    dlog = torch.empty(R, ld, dtype=torch.float32, device=DEV)
+    ops.softmax_ce_bwd(logits.to(DEV), labels.to(DEV), Cn, lse, coeff.to(DEV), dlog)
+    assert rel(dlog[:, :Cn], lr.grad) < 1e-5 and float(dlog[:, Cn:].abs().max()) == 0.0
+    x = torch.randn(32, 768, generator=g)
+    xr = x.clone().requires_grad_(True)
+    y_ref = O.l2_normalize(xr)
+    y, inv = torch.empty(32, 768, device=DEV), torch.empty(32, device=DEV)
+    ops.l2norm_fwd(x.to(DEV), y, inv)
+    assert rel(y, y_ref) < 1e-6
+    dy = torch.randn(32, 768, generator=g)
+    y_ref.backward(dy)
+    dx = torch.empty(32, 768, device=DEV)
+    ops.l2norm_bwd(dy.to(DEV), y, inv, dx)
+    assert rel(dx, xr.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K12 masking: bit-exact given injected draws (integer path)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,L,spanbert,use_attn", [(8, 128, True, True), (3, 32, True, True), (4, 128, False, True),
+                                                   (2, 64, True, False), (2, 1024, True, True)])
+def test_mask_inputs_bit_exact(ops, tiny_cfg, B, L, spanbert, use_attn):
+    cfg = dict(tiny_cfg, masking_do_spanbert=spanbert, masking_use_attn=use_attn)
+    g = torch.Generator().manual_seed(L + B)
+    ids = torch.randint(100, 50370, (B, L), generator=g, dtype=torch.int32)
+    ids[:, ::32] = O.START
+    ids[:, -L // 8:] = 0
+    summ = torch.rand(B, L, generator=g) * 12
+    summ[:, 5] = summ[:, 9]  # force an exact tie: tf.math.top_k keeps the lower index
+    k = int(L * 0.2)
+    draws = O.make_mask_draws(B, L, k, 50370, seed=B)
+    ref = O.mask_inputs(ids, summ if use_attn else None, cfg, draws)
+    if use_attn:
+        w = torch.tensor([1.0, 0.0]) * np.float32(ref["topk_val"] - 0.01) + np.float32(0.01)
+        consts = (float(np.float32(ref["topk_val"] - 0.01)), float(np.float32(0.01)), float(torch.log(w)[0]), float(torch.log(w)[1]),
+                  float(w.max()))
+    else:
+        consts = (0.0, 1.0, 0.0, 0.0, 1.0)
+    m_ids = torch.empty(B, L, dtype=torch.int32, device=DEV)
+    m_idx = torch.empty(B, k, dtype=torch.int32, device=DEV)
+    ops.mask_inputs(ids.to(DEV), summ.to(DEV) if use_attn else None, {k_: v.to(DEV) for k_, v in draws.items()}, m_ids, m_idx, None,
+                    int(L * 0.2), k, spanbert, O.MASK, consts)
+    assert torch.equal(m_idx.cpu(), ref["masked_idx"])
+    assert torch.equal(m_ids.cpu(), ref["masked_ids"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K10 AdamW: packed bf16 moments bit-exact over many steps, parameters to 1e-6
+# ---------------------------------------------------------------------------------------------------------------
+def test_adamw_vs_oracle(ops):
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    cfg = dict(learning_rate=3e-4, num_train_steps=1000, num_warmup_steps=10, weight_decay_rate=0.1, beta_2=0.98, epsilon=1e-6,
+               use_bfloat16_adam=True, param_overrides=[[["bias"], {"weight_decay_rate": 0}]])
+    p_ref = {"w/kernel": torch.randn(n, generator=g) * 0.02, "w/bias": torch.randn(n, generator=g) * 0.02}
+    opt = O.AdamOracle(p_ref, cfg)
+    dev = {k: dict(p=v.clone().to(DEV), m=torch.zeros(n, dtype=torch.bfloat16, device=DEV),
+                   v=torch.zeros(n, dtype=torch.bfloat16, device=DEV), pb=torch.zeros(n, dtype=torch.bfloat16, device=DEV))
+           for k, v in p_ref.items()}
+    for step in range(25):
+        grads = {k: torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-6, 1, (1,), generator=g))) for k in p_ref}
+        s = opt.step_scalars()
+        opt.apply_gradients(p_ref, grads)
+        for k, d in dev.items():
+            gd = grads[k].to(DEV)
+            wd = 0.1 if "kernel" in k else 0.0
+            ops.adamw_step(d["p"], gd, d["m"], d["v"], d["pb"], n, float(s["beta1"]), float(np.float32(1) - s["beta1"]),
+                           float(s["beta2"]), float(np.float32(1) - s["beta2"]), float(s["eps"]), float(s["lr_t"]), wd, 1.0, True)
+            assert float(gd.abs().max()) == 0.0  # zero_grad
+    for k, d in dev.items():
+        assert torch.equal(d["m"].cpu(), opt.m[k]), "first moment must be bit-exact"
+        assert torch.equal(d["v"].cpu(), opt.v[k]), "packed second moment must be bit-exact"
+        assert (d["p"].cpu() - p_ref[k]).abs().max().item() < 1e-6
+        assert torch.equal(d["pb"].cpu(), d["p"].cpu().bfloat16())

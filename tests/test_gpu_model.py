@@ -1,0 +1,181 @@
+"""GPU parity of the whole hot path through the MerlotModel mirror (pytest -m gpu): forward activations, the three
+losses, every parameter gradient, one optimizer step -- against the oracle on identical weights and inputs (dropout 0);
+plus size-independent properties at merlot.yaml's full sizes."""
+import pytest
+import torch
+
+from oracle import merlot_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def synth(cfg, batch, nc, Lc, h0, w0, seed):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(batch * nc, h0, w0, 3, generator=g).bfloat16().float()
+    ids = torch.randint(100, cfg["vocab_size"], (batch, nc, Lc), generator=g)
+    ids[:, :, 0] = O.START
+    lens = torch.randint(Lc // 2, Lc + 1, (batch, nc), generator=g)
+    ids = (ids * (torch.arange(Lc)[None, None] < lens[..., None])).int()
+    ncg = cfg["num_chunks_in_group"]
+    B = batch * nc // ncg
+    shuf = torch.arange(ncg).repeat(B)
+    shuf[:ncg] = 16 + torch.randperm(ncg, generator=g)
+    if B > 1:
+        shuf[ncg:2 * ncg] = 64 + torch.randperm(ncg, generator=g)
+    vid = torch.zeros(B, ncg, dtype=torch.int32)
+    vid[0, ncg // 2:] = 1
+    return image, ids, shuf.int(), vid
+
+
+def build(cfg, seed=1):
+    from merlot_b200.params import ParamStore
+    params = O.init_params(cfg, seed=seed, perturb=0.05)
+    # GEMM operands are the bf16 compute copies (bfloat16_getter): hand the oracle the same rounded matrices
+    params = {k: (v.bfloat16().float() if (k.endswith("kernel") or k.endswith("word_embeddings")) else v) for k, v in params.items()}
+    ocfg = dict(type="adam_optimizer", learning_rate=3e-4, num_train_steps=1000, num_warmup_steps=10, weight_decay_rate=0.1,
+                beta_2=0.98, clip_norm=0.0, use_bfloat16_adam=True,
+                param_overrides=[[["LayerNorm", "layer_norm", "GroupNorm", "bias"], {"weight_decay_rate": 0}]])
+    store = ParamStore(cfg, device=DEV, optimizer_cfg=ocfg)
+    store.load_tf_dict(params)
+    return params, store, ocfg
+
+
+def test_pretrain_step_parity(tiny_cfg):
+    from merlot_b200.modeling import MerlotModel
+    from merlot_b200.optimization import build_optimizer_from_config
+    cfg = tiny_cfg
+    batch, nc, Lc = 2, 4, 16
+    image, ids, shuf, vid = synth(cfg, batch, nc, Lc, 64, 96, 0)
+    params, store, ocfg = build(cfg)
+    B, Lj = batch * nc // cfg["num_chunks_in_group"], Lc * cfg["num_chunks_in_group"]
+    draws = O.make_mask_draws(B, Lj, int(Lj * 0.2), cfg["vocab_size"], seed=5)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_draws=draws)
+    assert rel(m.lang_transformer_info["attention_summs"], om.attention_summs) < 2e-3
+    gm = {"masked_ids": m.lang_mask_info["masked_ids"].cpu().reshape(B, Lj), "masked_idx": m.lang_mask_info["masked_idx"].cpu()}
+    if not (torch.equal(gm["masked_ids"], om.lang_mask_info["masked_ids"]) and torch.equal(gm["masked_idx"], om.lang_mask_info["masked_idx"])):
+        om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)  # near-tie in attn sums
+    for name in ("viz", "lang"):
+        assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 1e-2  # rel-Frobenius, bf16 stacks
+    ll, linfo = m.mask_loss()
+    cl, cinfo = m.contrastive_loss()
+    tl, tinfo = m.temporal_loss(shuf.to(DEV), vid.to(DEV))
+    total_ref, oinfo = O.pretrain_losses(om, shuf, vid)
+    for a, b in [(ll, oinfo["lang"]["loss"]), (cinfo["lang_to_viz"], oinfo["contr"]["lang_to_viz"]),
+                 (cinfo["viz_to_lang"], oinfo["contr"]["viz_to_lang"]), (cl, oinfo["contr"]["loss_all"]),
+                 (tinfo["lang_viz_loss"], oinfo["temporal"]["lang_viz_loss"]), (tinfo["viz_viz_loss"], oinfo["temporal"]["viz_viz_loss"]),
+                 (tl, oinfo["temporal"]["loss"])]:
+        assert abs(float(a) - float(b)) <= 2e-3 * abs(float(b)), (float(a), float(b))
+    total = float(ll) + float(cl) + float(tl)
+    assert abs(total - float(total_ref)) <= 1e-3 * abs(float(total_ref))  # north-star bar: losses within 1e-3 rel
+    assert float(tinfo["lang_viz_acc"]) == pytest.approx(float(oinfo["temporal"]["lang_viz_acc"]), abs=1e-6)
+    store.g.zero_()
+    m.backward()
+    total_ref.backward()
+    grads = store.to_tf_dict("g")
+    for k, v in leaf.items():
+        if v.grad is None or float(v.grad.norm()) < 1e-7:  # key biases: softmax is shift invariant => exactly zero gradient
+            continue
+        assert rel(grads[k], v.grad) < 4e-2, k
+    # one AdamW step on those gradients vs the oracle optimizer fed the GPU gradients (isolates K10 from bf16 noise)
+    opt, _ = build_optimizer_from_config(None, ocfg, None, store=store)
+    p_before = {k: v.clone() for k, v in store.to_tf_dict("p").items()}
+    adam = O.AdamOracle(p_before, ocfg)
+    adam.apply_gradients(p_before, {k: v for k, v in grads.items()})
+    opt.apply_gradients()
+    after = store.to_tf_dict("p")
+    for k in after:
+        assert (after[k] - p_before[k]).abs().max().item() < 2e-6, k
+    assert float(store.g.abs().max()) == 0.0 and store.global_step == 1
+
+
+def test_forward_only_2d_ids_config1(tiny_cfg):
+    """BASELINE config 1 shape family: 2-D input_ids => num_chunks = 1 (model/modeling.py:72-77), no masking, no losses."""
+    from merlot_b200.modeling import MerlotModel
+    cfg = dict(tiny_cfg)
+    image, ids, _, _ = synth(cfg, 3, 1, 16, 64, 96, 2)
+    params, store, _ = build(cfg, seed=3)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids[:, 0].to(DEV), params=store)
+    om = O.MerlotOracle(cfg, params, image, ids[:, 0])
+    assert m.num_chunks == 1 and m.B == 3 and m.L == 16 and m.P == om.P
+    for name in ("viz", "lang"):
+        assert m.encoder_hidden_states[name].shape == om.encoder_hidden_states[name].shape
+        assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 1e-2
+    with pytest.raises(ValueError):
+        MerlotModel(cfg, False, False, image.to(DEV), ids[0, 0].to(DEV), params=store)  # rank-1 ids: assert_rank ValueError
+    with pytest.raises(AssertionError):
+        MerlotModel(cfg, False, False, image[:, :60].to(DEV), ids[:, 0].to(DEV), params=store)  # h % patch != 0
+
+
+def test_sort_story_temporal_head_config4_shape(tiny_cfg):
+    """downstream/sort_story/get_zero_shot_logits.py:55-86: eval forward, shuffled idx + 64, all-pairs temporal softmax."""
+    from merlot_b200.modeling import MerlotModel
+    cfg = dict(tiny_cfg, num_chunks_in_group=5)
+    image, ids, _, _ = synth(cfg, 2, 5, 16, 64, 64, 4)
+    params, store, _ = build(cfg, seed=5)
+    shuf = (torch.stack([torch.randperm(5, generator=torch.Generator().manual_seed(i)) for i in range(2)]) + 64).int().reshape(-1)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=False,
+                    shuffled_idx_img=shuf.to(DEV), params=store)
+    om = O.MerlotOracle(cfg, params, image, ids, mask_input=False, shuffled_idx_img=shuf)
+    H = cfg["hidden_size"]
+    h_lang = m.encoder_hidden_states["lang"].reshape(m.B, 5, m.lang_chunk_length, H)[:, :, 0]
+    h_viz = m.encoder_hidden_states["viz"].reshape(m.B, 5, m.viz_chunk_length, H)[:, :, 0]
+    logits = m.allpairs_temporal_logits(h_lang, h_viz, scope_name="lang_viz_temporal")
+    ol = om.encoder_hidden_states["lang"].reshape(om.B, 5, om.lang_chunk_length, H)[:, :, 0]
+    ov = om.encoder_hidden_states["viz"].reshape(om.B, 5, om.viz_chunk_length, H)[:, :, 0]
+    ref = om.allpairs_temporal_logits(ol, ov, "lang_viz_temporal")
+    assert logits.shape == ref.shape == (2 * 25, 4)
+    assert rel(torch.softmax(logits.float(), -1)[:, 1:], torch.softmax(ref, -1)[:, 1:]) < 1e-2
+
+
+def test_dropout_training_mode_is_deterministic_and_changes_output(tiny_cfg):
+    from merlot_b200.modeling import MerlotModel
+    image, ids, shuf, vid = synth(tiny_cfg, 2, 4, 16, 64, 96, 0)
+    _, store, _ = build(tiny_cfg)
+    outs = []
+    for seed in (11, 11, 12):
+        m = MerlotModel(tiny_cfg, is_training=True, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=False,
+                        shuffled_idx_img=shuf.to(DEV), params=store, dropout_seed=seed)
+        outs.append(m.encoder_hidden_states["lang"].clone())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+
+
+def test_full_size_properties():
+    """merlot.yaml sizes (BASELINE configs[1], batch 2 to stay quick): finite losses at the random-init levels the
+    closed forms predict, backward linearity (grad arena accumulates: two backwards == 2x), and loss decreases on a fixed batch."""
+    import math
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from merlot_b200.train import model_fn_builder, synthetic_batch
+    cfg = bench.load_config()
+    cfg.model["hidden_dropout_prob"] = 0.0
+    cfg.optimizer["num_warmup_steps"] = 0
+    fn = model_fn_builder(cfg)
+    feats = synthetic_batch(cfg, 2, seed=0)
+    spec = fn(feats)
+    lang, contr, temp = (float(x) for x in spec.loss_parts)
+    assert abs(lang - math.log(50370)) < 0.5  # random-init MLM loss ~ ln(V)
+    assert 0.0 < contr < 0.25 * 2 * math.log(8) + 1.0 and math.isfinite(temp)
+    store = fn.store
+    store.g.zero_()
+    spec.model.backward()
+    g1 = store.g.clone()
+    spec.model.backward()
+    assert rel(store.g, 2 * g1) < 2e-3  # atomics reorder fp32 sums; linear accumulation otherwise
+    assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
+    store.g.zero_()
+    l0 = spec.loss
+    for _ in range(8):
+        s = fn(feats)
+        s.train_op()
+    assert fn(feats).loss < l0  # the step trains
