@@ -118,7 +118,7 @@ def test_forward_only_2d_ids_config1(tiny_cfg):
 def test_sort_story_temporal_head_config4_shape(tiny_cfg):
     """downstream/sort_story/get_zero_shot_logits.py:55-86: eval forward, shuffled idx + 64, all-pairs temporal softmax."""
     from merlot_b200.modeling import MerlotModel
-    cfg = dict(tiny_cfg, num_chunks_in_group=5)
+    cfg = dict(tiny_cfg, num_chunks_in_group=5, max_position_embeddings=128)
     image, ids, _, _ = synth(cfg, 2, 5, 16, 64, 64, 4)
     params, store, _ = build(cfg, seed=5)
     shuf = (torch.stack([torch.randperm(5, generator=torch.Generator().manual_seed(i)) for i in range(2)]) + 64).int().reshape(-1)
