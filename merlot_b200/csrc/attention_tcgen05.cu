@@ -43,10 +43,23 @@ __device__ __forceinline__ float masked_score(float s, float sc2, bool vq, bool 
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// forward
+// forward.  One CTA per (128-query tile, head, batch); 128 threads = one thread per TMEM lane = one query row.
+// Per 128-key tile:  S = Q K^T (tcgen05) -> the whole S row is read ONCE into registers -> masked online softmax with
+// register bitmasks for key validity -> P (bf16) into a swizzled smem A tile -> O += P V accumulated IN TMEM.
+// The running maximum is only advanced when it grows by more than 2^8 (lazy rescale: O is then corrected in TMEM with
+// tcgen05.ld/st), so the common iteration never touches O.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = 16384 * 3 + 32768 + 1024 + 128;
+constexpr int FWD_SMEM = 16384 * 3 + 32768 + 1024 + 1024;
+constexpr int MAX_MASK_WORDS = 128;  // key-validity bitmask for up to 4096 keys
+constexpr float MASKED_LOG2 = -1e10f * LOG2E;
 
+// bitmask of in-range keys for the 32-key word starting at key k
+__device__ __forceinline__ uint32_t range_word(int k, int S) {
+  const int n = S - k;
+  return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+}
+
+template <bool HAS_MASK>
 __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -54,11 +67,12 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   uint8_t* sK = smem + 16384;
   uint8_t* sV = smem + 32768;
   uint8_t* sP = smem + 49152;  // [128 q rows][128 keys] bf16, two 64-key K-major atoms of 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 32768);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 49152 + 32768);  // [MAX_MASK_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 32768 + 512);
   uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
@@ -70,6 +84,13 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  if (HAS_MASK) {  // key validity of this batch element as a bitmask (bit k%32 of word k/32)
+    for (int k = tid; k < n_kv * AT_N; k += 128) {
+      const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
+      const uint32_t w = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_mask[k >> 5] = w;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -88,18 +109,17 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 
   const int q = q0 + tid;
   const bool q_in = q < S;
-  const bool vq = q_in ? (p.valid ? p.valid[tok0 + q] != 0 : true) : true;
-  float m_run = -INFINITY, l_run = 0.f;
-  float o[AT_D];
-#pragma unroll
-  for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+  const bool vq = (HAS_MASK && q_in) ? (p.valid[tok0 + q] != 0) : true;
+  // a padding QUERY row softmaxes uniformly over all in-range keys: realised as zero scores with every key "valid"
+  const float sc2 = vq ? p.scale * LOG2E : 0.f;
+  float m_used = -INFINITY, l_run = 0.f;
 
   constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
-  const float sc2 = p.scale * LOG2E;
 
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
+    const int k0 = j * AT_N;
     if (tid == 0) {
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(bar_k, ph);
@@ -115,57 +135,68 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
       mbar_arrive_expect_tx(bar_k, 16384);
       tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + (j + 1) * AT_N);
     }
-    const int k0 = j * AT_N;
-    // ---- pass A: row max of the masked, scaled scores (log2 domain) ----
+    // ---- S row -> registers (log2 domain), masked; row maximum ----
+    float x[AT_N];
     float mx = -INFINITY;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tS + lane_off + c * 32, r);
       tmem_wait_ld();
+      const uint32_t iw = range_word(k0 + c * 32, S);
+      const uint32_t vw = (HAS_MASK && vq) ? s_mask[(k0 >> 5) + c] : 0xffffffffu;
+      if (iw == 0xffffffffu && vw == 0xffffffffu) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int kk = k0 + c * 32 + i;
-        const bool in = kk < S;
-        const bool vk = in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
-        float x = masked_score(__uint_as_float(r[i]), sc2, vq, vk, in);
-        mx = fmaxf(mx, x);
+        for (int i = 0; i < 32; ++i) {
+          x[c * 32 + i] = __uint_as_float(r[i]) * sc2;
+          mx = fmaxf(mx, x[c * 32 + i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(r[i]) * sc2;
+          t = ((vw >> i) & 1u) ? t : MASKED_LOG2;
+          t = ((iw >> i) & 1u) ? t : -INFINITY;
+          x[c * 32 + i] = t;
+          mx = fmaxf(mx, t);
+        }
       }
     }
-    const float m_new = fmaxf(m_run, mx);
-    const float alpha = exp2f(m_run - m_new);  // m_run = -inf on the first tile -> 0
+    // ---- lazy running max: advance (and correct O in TMEM) only when the row max grew by more than 2^8 ----
+    const bool need = mx > m_used + 8.0f;  // always true on the first tile (m_used = -inf)
+    if (j > 0 && __any_sync(0xffffffffu, need)) {
+      const float f = need ? ex2_approx(m_used - mx) : 1.0f;
+#pragma unroll
+      for (int c = 0; c < AT_D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tO + lane_off + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+        tmem_st_32x32(tO + lane_off + c * 32, r);
+      }
+      tmem_wait_st();
+      l_run *= f;
+    }
+    if (need) m_used = mx;
+    // ---- p = 2^(x - m), P (bf16) into the K-major swizzled A tile ----
     float rowsum = 0.f;
-    // ---- pass B: p = 2^(x - m), write P (bf16) into the K-major swizzled A tile ----
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tS + lane_off + c * 32, r);
-      tmem_wait_ld();
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        float pv[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int kk = k0 + c * 32 + i + u;
-          const bool in = kk < S;
-          const bool vk = in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
-          float x = masked_score(__uint_as_float(r[i + u]), sc2, vq, vk, in);
-            pv[u] = exp2f(x - m_new);
-          rowsum += pv[u];
-        }
-        pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+        const float p0 = ex2_approx(x[c * 32 + i] - m_used), p1 = ex2_approx(x[c * 32 + i + 1] - m_used);
+        rowsum += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
       }
       uint8_t* atom = sP + (c >> 1) * 16384;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t chunk = (uint32_t)((c & 1) * 4 + g);
-        *reinterpret_cast<uint4*>(atom + sw128_offset(tid, chunk)) =
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(atom + sw128_offset(tid, (uint32_t)((c & 1) * 4 + g))) =
             make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-      }
     }
-    l_run = l_run * alpha + rowsum;
-    m_run = m_new;
+    l_run += rowsum;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -178,65 +209,70 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
       for (int k = 0; k < AT_N / 16; ++k) {
         const uint64_t da = desc_kmajor(pa + (k >> 2) * 16384, k & 3);
         const uint64_t db = desc_mnmajor(va, k, 0);  // single 64-wide chunk: LBO unused
-        umma_bf16_ss(tO, da, db, idesc_o, k > 0);
+        umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
       }
       umma_commit(bar_o);
     }
-    mbar_wait(bar_o, ph);
+    mbar_wait(bar_o, ph);  // P smem, V smem and O are consistent again
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // V tile is free once O_j = P V has completed
+    if (tid == 0 && j + 1 < n_kv) {
       mbar_arrive_expect_tx(bar_v, 16384);
       tma_load_2d(sV, &tm_qkv, bar_v, 2 * H + h * AT_D, tok0 + (j + 1) * AT_N);
     }
+  }
+
+  {
+    const float inv = 1.0f / l_run;
+    bf16* dst = p.ctx + (size_t)(tok0 + q) * p.ld_ctx + h * AT_D;
 #pragma unroll
     for (int c = 0; c < AT_D / 32; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tO + lane_off + c * 32, r);
       tmem_wait_ld();
+      if (q_in) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * inv, __uint_as_float(r[g * 8 + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv));
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+        }
+      }
     }
-    tc_fence_before();
+    if (q_in && p.lse) p.lse[((size_t)b * p.heads + h) * S + q] = (m_used + log2f(l_run)) * LN2;
   }
-
-  if (q_in) {
-    const float inv = 1.0f / l_run;
-    bf16* dst = p.ctx + (size_t)(tok0 + q) * p.ld_ctx + h * AT_D;
-#pragma unroll
-    for (int g = 0; g < AT_D / 8; ++g) {
-      uint4 pk = make_uint4(pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv), pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv),
-                            pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv), pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv));
-      *reinterpret_cast<uint4*>(dst + g * 8) = pk;
-    }
-    if (p.lse) p.lse[((size_t)b * p.heads + h) * S + q] = (m_run + log2f(l_run)) * LN2;
-  }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// backward: one CTA per (key tile, head, batch); loops over query tiles.
+// backward: one CTA per (key tile, head, batch); loops over query tiles (double-buffered Q/dO, prefetched by TMA).
 //   S^T = K Q^T, dP^T = V dO^T (keys on TMEM lanes) -> P^T, dS^T in smem -> dV += P^T dO, dK += dS^T Q, dQ_i = dS K
+// The S^T/dP^T MMAs of tile i+1 are issued right behind the dV/dK/dQ MMAs of tile i, so the tensor pipe works while the
+// threads red.add the dQ partial of tile i.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 16384 * 4 + 32768 * 2 + 1024 + 1024 + 128;
+constexpr int BWD_SMEM = 16384 * 2 + 32768 * 2 + 32768 * 2 + 2048 + 1024 + 1024;
 
+template <bool HAS_MASK>
 __global__ void __launch_bounds__(128, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQ = smem + 32768;
-  uint8_t* sdO = smem + 49152;
-  uint8_t* sPT = smem + 65536;        // P^T  [128 keys][128 q] bf16, two 64-col atoms
-  uint8_t* sdST = smem + 65536 + 32768;  // dS^T same layout
-  float* s_lse = reinterpret_cast<float*>(smem + 65536 + 65536);
-  float* s_dsum = s_lse + 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 65536 + 1024);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1, *bar_1 = bars + 2, *bar_2 = bars + 3;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint8_t* sQd = smem + 32768;            // 2 x { Q tile 16 KB, dO tile 16 KB }
+  uint8_t* sPT = smem + 32768 + 65536;    // P^T  [128 keys][128 q] bf16, two 64-col atoms
+  uint8_t* sdST = sPT + 32768;            // dS^T same layout
+  float* s_nlse = reinterpret_cast<float*>(sdST + 32768);  // [2][128]  -lse * log2(e)
+  float* s_dsum = s_nlse + 256;                            // [2][128]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 256);  // [MAX_MASK_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_mask) + 512);
+  uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [2] */, *bar_1 = bars + 3, *bar_2 = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
@@ -244,10 +280,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_1, 1); mbar_init(bar_2, 1);
+    mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_1, 1); mbar_init(bar_2, 1);
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (HAS_MASK) {
+    for (int k = tid; k < n_q * AT_M; k += 128) {
+      const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
+      const uint32_t w = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_mask[k >> 5] = w;
+    }
+  }
+  auto stage_stats = [&](int i) {  // -lse*log2e and D of query tile i -> smem buffer i&1
+    const int q = i * AT_M + tid;
+    const size_t o = ((size_t)b * p.heads + h) * S + q;
+    s_nlse[(i & 1) * 128 + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
+    s_dsum[(i & 1) * 128 + tid] = (q < S) ? p.dsum[o] : 0.f;
+  };
+  stage_stats(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -255,46 +305,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
+  constexpr uint32_t idesc_st = make_idesc_bf16(AT_N, AT_M, 0, 0);   // S^T, dP^T : both operands K-major (d)
+  constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
+  constexpr uint32_t idesc_dq = make_idesc_bf16(AT_M, AT_D, 1, 1);   // A = dS (MN-major view of dS^T), B = K MN-major
+
+  auto load_q = [&](int i) {
+    uint8_t* buf = sQd + (i & 1) * 32768;
+    mbar_arrive_expect_tx(&bar_q[i & 1], 32768);
+    tma_load_2d(buf, &tm_qkv, &bar_q[i & 1], h * AT_D, tok0 + i * AT_M);
+    tma_load_2d(buf + 16384, &tm_do, &bar_q[i & 1], h * AT_D, tok0 + i * AT_M);
+  };
+  auto issue_st = [&](int i) {  // S^T and dP^T of query tile i
+    mbar_wait(&bar_q[i & 1], (uint32_t)((i >> 1) & 1));
+    tc_fence_after();
+    const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQd + (i & 1) * 32768), da = qa + 16384;
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
+    umma_commit(bar_1);
+  };
+
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_kv, 32768);
     tma_load_2d(sK, &tm_qkv, bar_kv, H + h * AT_D, tok0 + k0);
     tma_load_2d(sV, &tm_qkv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
+    load_q(0);
+    if (n_q > 1) load_q(1);
+    mbar_wait(bar_kv, 0);
+    issue_st(0);
   }
   const int kk = k0 + tid;  // this thread's key row
   const bool k_in = kk < S;
-  const bool vk = k_in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
-
-  constexpr uint32_t idesc_st = make_idesc_bf16(AT_N, AT_M, 0, 0);   // S^T, dP^T : both operands K-major (d)
-  constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
-  constexpr uint32_t idesc_dq = make_idesc_bf16(AT_M, AT_D, 1, 1);   // A = dS (MN-major view of dS^T), B = K MN-major
+  const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
   const float sc2 = p.scale * LOG2E;
 
   for (int i = 0; i < n_q; ++i) {
     const uint32_t ph = i & 1;
     const int q0 = i * AT_M;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_q, 32768);
-      tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
-      tma_load_2d(sdO, &tm_do, bar_q, h * AT_D, tok0 + q0);
-    }
-    {  // stage lse / D for this query tile
-      const int q = q0 + tid;
-      const size_t o = ((size_t)b * p.heads + h) * S + q;
-      s_lse[tid] = (q < S) ? p.lse[o] * LOG2E : 0.f;
-      s_dsum[tid] = (q < S) ? p.dsum[o] : 0.f;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (i == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph);
-      tc_fence_after();
-      const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQ), da = smem_u32(sdO);
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
-      umma_commit(bar_1);
-    }
+    const float* nlse = s_nlse + (i & 1) * 128;
+    const float* dsm = s_dsum + (i & 1) * 128;
     mbar_wait(bar_1, ph);
     tc_fence_after();
 #pragma unroll 1
@@ -303,23 +353,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_ld_32x32(tST + lane_off + c * 32, rs);
       tmem_ld_32x32(tdPT + lane_off + c * 32, rd);
       tmem_wait_ld();
+      const uint32_t iw = k_in ? range_word(q0 + c * 32, S) : 0u;           // query in range (and this key in range)
+      const uint32_t qw = HAS_MASK ? s_mask[(q0 >> 5) + c] : 0xffffffffu;   // query validity
+      const bool fast = (iw == 0xffffffffu) && (qw == 0xffffffffu) && vk;
       uint32_t pk[16], dk[16];
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float pv[2], dv[2];
+      for (int e = 0; e < 32; e += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(nlse + c * 32 + e);
+        const float4 d4 = *reinterpret_cast<const float4*>(dsm + c * 32 + e);
+        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+        float pv[4], dv[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int ql = c * 32 + e + u;
-          const int q = q0 + ql;
-          const bool q_in = q < S;
-          const bool vq = q_in ? (p.valid ? p.valid[tok0 + q] != 0 : true) : true;
-          float x = masked_score(__uint_as_float(rs[e + u]), sc2, vq, vk, k_in);
-          float pr = (q_in && k_in) ? exp2f(x - s_lse[ql]) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          float t = __uint_as_float(rs[e + u]) * sc2;
+          if (!fast) {
+            t = vk ? t : MASKED_LOG2;
+            t = ((qw >> (e + u)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
+          }
+          float pr = ex2_approx(t + ls[u]);
+          if (!fast) pr = ((iw >> (e + u)) & 1u) ? pr : 0.f;
           pv[u] = pr;
-          dv[u] = pr * (__uint_as_float(rd[e + u]) - s_dsum[ql]) * p.scale;
+          dv[u] = (__uint_as_float(rd[e + u]) - ds[u]) * (pr * p.scale);
         }
-        pk[e >> 1] = pack_bf16x2(pv[0], pv[1]);
-        dk[e >> 1] = pack_bf16x2(dv[0], dv[1]);
+        pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+        dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -328,12 +385,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
       }
     }
+    if (i + 1 < n_q) stage_stats(i + 1);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQ), da = smem_u32(sdO), ka = smem_u32(sK);
+      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQd + (i & 1) * 32768), da = qa + 16384,
+                     ka = smem_u32(sK);
 #pragma unroll
       for (int k = 0; k < AT_M / 16; ++k)  // dV += P^T dO   (contraction over q)
         umma_bf16_ss(tdV, desc_kmajor(pa + (k >> 2) * 16384, k & 3), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
@@ -344,9 +403,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       for (int k = 0; k < AT_N / 16; ++k)  // dQ_i = dS K      (contraction over keys; A = MN-major view of dS^T)
         umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 16384), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);
       umma_commit(bar_2);
+      if (i + 1 < n_q) issue_st(i + 1);  // keeps the tensor pipe busy during the dQ reduction below
     }
     mbar_wait(bar_2, ph);
     tc_fence_after();
+    if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
     {  // dQ partial: lanes are query rows here
       const int q = q0 + tid;
 #pragma unroll
@@ -366,7 +427,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
     tc_fence_before();
-    __syncthreads();  // sQ/sdO/s_lse reuse + TMEM S^T/dP^T/dQ reuse by the next iteration
+    __syncthreads();  // dQ TMEM / P^T, dS^T smem reuse by the next iteration
   }
   // ---- dK, dV for this key tile (exclusive rows) ----
   tc_fence_after();
@@ -567,10 +628,16 @@ extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
   CUtensorMap tm;
   rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, 128);
   if (rc) return rc;
+  MB_REQUIRE(a->S <= MAX_MASK_WORDS * 32 - AT_N, MERLOT_ESHAPE, "attention_fwd: sequence longer than %d keys", MAX_MASK_WORDS * 32 - AT_N);
   static bool attr = false;
-  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM)); attr = true; }
+  if (!attr) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
   dim3 grid(ceil_div(a->S, AT_M), a->heads, a->B);
-  attn_fwd_kernel<<<grid, 128, FWD_SMEM, stream>>>(tm, p);
+  if (a->valid) attn_fwd_kernel<true><<<grid, 128, FWD_SMEM, stream>>>(tm, p);
+  else attn_fwd_kernel<false><<<grid, 128, FWD_SMEM, stream>>>(tm, p);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
@@ -598,10 +665,16 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tdo, a->d_ctx, (uint64_t)a->ld_ctx, (uint64_t)tokens, (uint64_t)a->ld_ctx, 64, 128);
   if (rc) return rc;
+  MB_REQUIRE(a->S <= MAX_MASK_WORDS * 32 - AT_M, MERLOT_ESHAPE, "attention_bwd: sequence longer than %d keys", MAX_MASK_WORDS * 32 - AT_M);
   static bool attr = false;
-  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM)); attr = true; }
+  if (!attr) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr = true;
+  }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  attn_bwd_kernel<<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
+  if (a->valid) attn_bwd_kernel<true><<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
+  else attn_bwd_kernel<false><<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
   MB_CHECK_LAUNCH();
   {
     const long long n = tokens * (H / 8);

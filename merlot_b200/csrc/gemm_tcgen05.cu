@@ -14,9 +14,11 @@
 namespace mb {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle atom
-constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BUDGET = 196608;  // operand ring; + 1024 alignment slack + barriers
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SMEM_LIMIT = 232448 - 1024 - 256;  // 227 KB minus alignment slack and barriers
+constexpr int STAGING_BYTES = 65536;             // 4 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
 
 struct GemmDev {
   int M, N, K;
@@ -32,22 +34,24 @@ struct GemmDev {
   uint32_t drop_thresh16; float drop_scale; uint64_t seed; uint32_t site;
 };
 
-template <int BN>
+template <int BN, bool TS>
 struct GemmCfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - (TS ? STAGING_BYTES : 0)) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512: power of two)
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + (TS ? STAGING_BYTES : 0) + 1024 + 256;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Epilogue for 8 consecutive columns [col, col+8) of one row. v[] holds alpha-unscaled accumulators.
-__device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, float (&v)[8]) {
+// Fused epilogue math for 8 consecutive columns [col, col+8) of one row, in registers.
+//   v = alpha*acc (+bias); GELU: pre <- v, v <- gelu(v); MUL_DGELU: v *= gelu'(aux); DROPOUT; (+resid)
+// `in_range` = row < M (global loads are skipped for padding rows; their results are clipped on store).
+__device__ __forceinline__ void epi_math8(const GemmDev& p, int row, int col, bool in_range, float (&v)[8], float (&pre)[8]) {
   const bool full = (col + 8 <= p.N);
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
@@ -64,32 +68,21 @@ __device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, fl
     }
   }
   if (p.flags & MERLOT_GEMM_GELU) {
-    if (p.out2 != nullptr) {  // keep the pre-activation for the backward pass
-      bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col;
-      if (full) {
-        uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                              pack_bf16x2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(o) = pk;
-      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) o[i] = __float2bfloat16_rn(v[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 8; ++i) { pre[i] = v[i]; v[i] = gelu_erf_fast(v[i]); }
   }
-  if (p.flags & MERLOT_GEMM_MUL_DGELU) {
+  if ((p.flags & MERLOT_GEMM_MUL_DGELU) && in_range) {
     const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
     if (full) {
       uint4 u = __ldg(reinterpret_cast<const uint4*>(a));
       float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      v[0] *= gelu_erf_grad(f0.x); v[1] *= gelu_erf_grad(f0.y); v[2] *= gelu_erf_grad(f1.x); v[3] *= gelu_erf_grad(f1.y);
-      v[4] *= gelu_erf_grad(f2.x); v[5] *= gelu_erf_grad(f2.y); v[6] *= gelu_erf_grad(f3.x); v[7] *= gelu_erf_grad(f3.y);
+      v[0] *= gelu_erf_grad_fast(f0.x); v[1] *= gelu_erf_grad_fast(f0.y); v[2] *= gelu_erf_grad_fast(f1.x);
+      v[3] *= gelu_erf_grad_fast(f1.y); v[4] *= gelu_erf_grad_fast(f2.x); v[5] *= gelu_erf_grad_fast(f2.y);
+      v[6] *= gelu_erf_grad_fast(f3.x); v[7] *= gelu_erf_grad_fast(f3.y);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) v[i] *= gelu_erf_grad(__bfloat162float(a[i]));
+        if (col + i < p.N) v[i] *= gelu_erf_grad_fast(__bfloat162float(a[i]));
     }
   }
   if (p.flags & MERLOT_GEMM_DROPOUT) {
@@ -98,7 +91,7 @@ __device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, fl
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.0f;
   }
-  if (p.resid != nullptr) {
+  if (p.resid != nullptr && in_range) {
     const bf16* r = p.resid + (size_t)row * p.ld_resid + col;
     if (full) {
       uint4 u = __ldg(reinterpret_cast<const uint4*>(r));
@@ -110,8 +103,23 @@ __device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, fl
         if (col + i < p.N) v[i] += __bfloat162float(r[i]);
     }
   }
-  // ---- store ----
-  const bool second = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
+}
+
+__device__ __forceinline__ void store_bf16x8(bf16* o, int col, int N, const float (&v)[8]) {
+  if (col + 8 <= N) {
+    *reinterpret_cast<uint4*>(o) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (col + i < N) o[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// direct (register -> global) store path: fp32 outputs, atomics, and bf16 fallbacks
+__device__ __forceinline__ void epi_store_direct(const GemmDev& p, int row, int col, const float (&v)[8], const float (&pre)[8]) {
+  const bool full = (col + 8 <= p.N);
+  const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
   if (p.flags & MERLOT_GEMM_OUT_F32) {
     float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ld_out + col;
     if (p.flags & MERLOT_GEMM_ATOMIC) {
@@ -123,43 +131,42 @@ __device__ __forceinline__ void epilogue8(const GemmDev& p, int row, int col, fl
         for (int i = 0; i < 8; ++i)
           if (col + i < p.N) atomicAdd(o + i, v[i]);
       }
-    } else {
-      if (full && ((p.ld_out & 3) == 0)) {
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) o[i] = v[i];
-      }
-    }
-  } else {
-    bf16* o = second ? reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ld_out2 + col
-                     : reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col;
-    if (full) {
-      uint4 pk = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                            pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(o) = pk;
+    } else if (full && ((p.ld_out & 3) == 0)) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) o[i] = __float2bfloat16_rn(v[i]);
+        if (col + i < p.N) o[i] = v[i];
     }
+  } else if (dual) {
+    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, pre);
+    store_bf16x8(reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ld_out2 + col, col, p.N, v);
+  } else {
+    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, v);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int chunk16, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)chunk16)) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// TS = true: bf16 outputs leave through 128B-swizzled smem staging boxes and TMA stores (fully coalesced, edge clipping
+// by the tensor map).  TS = false: direct register->global stores (fp32 outputs / atomics).
+template <int BN, bool A_MN, bool B_MN, bool TS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const GemmDev p) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tma_o1, const __grid_constant__ CUtensorMap tma_o2, const GemmDev p) {
+  using Cfg = GemmCfg<BN, TS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (TS ? STAGING_BYTES : 0));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -172,13 +179,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (TS) { tma_prefetch_desc(&tma_o1); tma_prefetch_desc(&tma_o2); }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -262,42 +270,115 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int lane_base = (warp & 3) * 32;  // TMEM lane window this warp may touch
+    // ===================== epilogue warps (2 .. 2+EPI_WARPS) =====================
+    const int e = warp - 2;
+    const int quad = warp & 3;          // TMEM lane window this warp may touch: lanes [32*quad, 32*quad+32)
+    const int half = e >> 2;            // which half of the tile's columns this warp owns
+    const int row_in_tile = quad * 32 + lane;
+    const bool issuer = (e == 0 && lane == 0);
+    const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
       const int n_blk = mn % p.n_blocks;
       const int m_blk = mn / p.n_blocks;
-      const int row = m_blk * BLOCK_M + lane_base + lane;
+      const int row = m_blk * BLOCK_M + row_in_tile;
+      const bool in_range = row < p.M;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)lane_base << 16);
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+      if (!TS) {
+        constexpr int CH = BN / 64;  // 32-column chunks per warp
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_wait_ld();
-        const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N) {
+        for (int c = 0; c < CH; ++c) {
+          uint32_t r[32];
+          const int tcol = half * (BN / 2) + c * 32;
+          tmem_ld_32x32(taddr + tcol, r);
+          tmem_wait_ld();
+          const int col0 = n_blk * BN + tcol;
+          if (in_range && col0 < p.N) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float v[8];
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col < p.N) {
+                float v[8], pre[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              epilogue8(p, row, col, v);
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                epi_math8(p, row, col, true, v, pre);
+                epi_store_direct(p, row, col, v, pre);
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      } else {
+        // single output: one phase, warp owns BN/2 columns -> boxes [half*BN/128 ...]; dual output (pre + act): BN/128
+        // phases of 128 accumulator columns, warp owns 64 of them -> pre box `half`, act box `2+half`.
+        const int phases = dual ? BN / 128 : 1;
+        const int chunks = dual ? 2 : BN / 64;  // 32-column chunks per warp per phase
+        for (int ph = 0; ph < phases; ++ph) {
+          if (issuer) tma_store_wait_read_all();        // staging is free again
+          named_bar_sync(1, 32 * EPI_WARPS);
+          const int tcol_base = dual ? ph * 128 + half * 64 : half * (BN / 2);
+#pragma unroll 1
+          for (int c = 0; c < chunks; ++c) {
+            uint32_t r[32];
+            const int tcol = tcol_base + c * 32;
+            tmem_ld_32x32(taddr + tcol, r);
+            tmem_wait_ld();
+            const int col0 = n_blk * BN + tcol;
+            const int box = dual ? half : (half * (BN / 128) + (c >> 1));
+            uint8_t* b1 = staging + box * 16384;
+            uint8_t* b2 = staging + (2 + half) * 16384;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              float v[8], pre[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+              if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
+              const int chunk16 = (c & 1) * 4 + g;
+              if (dual) {
+                stage_bf16x8(b1, row_in_tile, chunk16, pre);
+                stage_bf16x8(b2, row_in_tile, chunk16, v);
+              } else {
+                stage_bf16x8(b1, row_in_tile, chunk16, v);
+              }
+            }
+          }
+          if (ph == phases - 1) {  // all TMEM reads of this accumulator stage are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 32 * EPI_WARPS);
+          if (issuer) {
+            const int r0 = m_blk * BLOCK_M;
+            if (dual) {
+              const int c0 = n_blk * BN + ph * 128;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                if (c0 + h * 64 < p.N) {
+                  tma_store_2d(&tma_o1, staging + h * 16384, c0 + h * 64, r0);
+                  tma_store_2d(&tma_o2, staging + (2 + h) * 16384, c0 + h * 64, r0);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int b = 0; b < BN / 64; ++b)
+                if (n_blk * BN + b * 64 < p.N) tma_store_2d(&tma_o1, staging + b * 16384, n_blk * BN + b * 64, r0);
+            }
+            tma_store_commit();
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TS && issuer) tma_store_wait_all();  // global writes complete before the CTA exits
   }
 
   tc_fence_before();
@@ -313,11 +394,11 @@ struct ProfRec { cudaEvent_t e0, e1; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
-                            cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+template <int BN, bool A_MN, bool B_MN, bool TS>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1, const CUtensorMap& to2,
+                            const GemmDev& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, TS>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, TS>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
@@ -330,7 +411,7 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
     rec.flops = 2.0 * (double)p.M * (double)p.N * (double)p.K;
     MB_CHECK_CUDA(cudaEventRecord(rec.e0, stream));
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, to1, to2, p);
   MB_CHECK_LAUNCH();
   if (g_prof_on) {
     MB_CHECK_CUDA(cudaEventRecord(rec.e1, stream));
@@ -392,13 +473,14 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   p.num_kb = ceil_div(g->K, BLOCK_K);
   // ---- tile width: minimise wave-quantisation loss; BN=256 halves per-FLOP smem traffic so it wins ties ----
   int bn = g->block_n;
+  if (bn == 0 && (g->flags & MERLOT_GEMM_ATOMIC)) bn = 256;  // wgrad: split-K fills the machine, wide tiles halve smem traffic
   if (bn == 0) {
     double best = -1;
     for (int cand : {256, 128}) {
       long long tiles = (long long)p.m_blocks * ceil_div(g->N, cand);
       long long waves = ceil_div_ll(tiles, sms);
       double useful = (double)g->N / (double)(ceil_div(g->N, cand) * cand);
-      double eff = (double)tiles / (double)(waves * sms) * useful * (cand == 256 ? 1.0 : 0.93);
+      double eff = (double)tiles / (double)(waves * sms) * useful * (cand == 256 ? 1.0 : 0.80);
       if (eff > best + 1e-9) { best = eff; bn = cand; }
     }
   }
@@ -437,14 +519,32 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   const long long tiles = (long long)mn_tiles * p.splits;
   const int grid = (int)(tiles < sms ? tiles : sms);
 
-#define MB_GEMM_DISPATCH(BN_)                                                                   \
-  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true>(ta, tb, p, grid, stream);   \
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true>(ta, tb, p, grid, stream); \
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false>(ta, tb, p, grid, stream); \
-  return launch_gemm_inst<BN_, true, false>(ta, tb, p, grid, stream);
+  // bf16 outputs leave through TMA stores (swizzled smem staging); fp32 outputs / atomics use direct stores
+  const bool ts = !out_f32;
+  CUtensorMap to1, to2;
+  memset(&to1, 0, sizeof(to1));
+  memset(&to2, 0, sizeof(to2));
+  if (ts) {
+    const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
+    if (dual) MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
+    rc = make_tmap_bf16_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 64, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&to2, dual ? g->out2 : g->out, (uint64_t)g->N, (uint64_t)g->M,
+                           (uint64_t)(dual ? g->ld_out2 : g->ld_out), 64, BLOCK_M);
+    if (rc) return rc;
+  }
+#define MB_GEMM_DISPATCH2(BN_, TS_)                                                                                  \
+  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true, TS_>(ta, tb, to1, to2, p, grid, stream);   \
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true, TS_>(ta, tb, to1, to2, p, grid, stream); \
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false, TS_>(ta, tb, to1, to2, p, grid, stream); \
+  return launch_gemm_inst<BN_, true, false, TS_>(ta, tb, to1, to2, p, grid, stream);
+#define MB_GEMM_DISPATCH(BN_)             \
+  if (ts) { MB_GEMM_DISPATCH2(BN_, true) } \
+  MB_GEMM_DISPATCH2(BN_, false)
   if (bn == 256) { MB_GEMM_DISPATCH(256) }
   MB_GEMM_DISPATCH(128)
 #undef MB_GEMM_DISPATCH
+#undef MB_GEMM_DISPATCH2
 }
 
 extern "C" void merlot_gemm_profile_begin(void) {

@@ -201,14 +201,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * H + i] = sred[i];
 }
 
-// out[c] += sum_b partial[b][c]   (c in [0, n)); used for LN dgamma/dbeta
+// out[c] += sum_b partial[b][c]   (c in [0, n)); used for LN dgamma/dbeta.  grid = (ceil(n/256), RSPLIT): each thread sums
+// every RSPLIT-th partial row, then one fp32 atomic per thread.
+constexpr int RSPLIT = 16;
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int n, float* __restrict__ out0,
                                        float* __restrict__ out1, int half) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * n + c];
-  if (c < half) out0[c] += s; else out1[c - half] += s;
+  for (int b = blockIdx.y; b < nblocks; b += RSPLIT) s += partial[(size_t)b * n + c];
+  atomicAdd(c < half ? out0 + c : out1 + (c - half), s);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -466,7 +468,7 @@ extern "C" int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream_) {
   const uint32_t th = d->dropout_p > 0.f ? thresh16(d->dropout_p) : 0;
   const float sc = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
   long long want = ceil_div_ll(d->rows, 8);
-  const int grid = (int)(want < 4 * 148 ? want : 4 * 148);
+  const int grid = (int)(want < 2 * 148 ? want : 2 * 148);
   const size_t smem = (size_t)2 * d->H * sizeof(float);
   float* part = reinterpret_cast<float*>(d->workspace);
 #define LNB(TX, TDY, TDX)                                                                                                         \
@@ -481,7 +483,7 @@ extern "C" int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream_) {
   else return set_error(MERLOT_EINVAL, "layernorm_bwd: unsupported dtype combination x_f32=%d dy_f32=%d dx_f32=%d", d->x_f32, d->dy_f32, d->dx_f32);
 #undef LNB
   MB_CHECK_LAUNCH();
-  reduce_partials_kernel<<<ceil_div(2 * d->H, 256), 256, 0, st>>>(part, grid, 2 * d->H, d->dgamma, d->dbeta, d->H);
+  reduce_partials_kernel<<<dim3(ceil_div(2 * d->H, 256), RSPLIT), 256, 0, st>>>(part, grid, 2 * d->H, d->dgamma, d->dbeta, d->H);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
