@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 constexpr int BWD_SMEM = 16384 * 2 + 32768 * 2 + 32768 * 2 + 2048 + 1024 + 1024;
 
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -272,7 +272,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [2] */, *bar_1 = bars + 3, *bar_2 = bars + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
+  // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every tile's columns
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, quad = warp & 3, row_t = quad * 32 + lane;
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
@@ -285,17 +287,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
   if (HAS_MASK) {
-    for (int k = tid; k < n_q * AT_M; k += 128) {
+    for (int k = tid; k < n_q * AT_M; k += 256) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
       const uint32_t w = __ballot_sync(0xffffffffu, v);
       if (lane == 0) s_mask[k >> 5] = w;
     }
   }
   auto stage_stats = [&](int i) {  // -lse*log2e and D of query tile i -> smem buffer i&1
-    const int q = i * AT_M + tid;
-    const size_t o = ((size_t)b * p.heads + h) * S + q;
-    s_nlse[(i & 1) * 128 + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
-    s_dsum[(i & 1) * 128 + tid] = (q < S) ? p.dsum[o] : 0.f;
+    if (tid < 128) {
+      const int q = i * AT_M + tid;
+      const size_t o = ((size_t)b * p.heads + h) * S + q;
+      s_nlse[(i & 1) * 128 + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
+      s_dsum[(i & 1) * 128 + tid] = (q < S) ? p.dsum[o] : 0.f;
+    }
   };
   stage_stats(0);
   tc_fence_before();
@@ -303,7 +307,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
   constexpr uint32_t idesc_st = make_idesc_bf16(AT_N, AT_M, 0, 0);   // S^T, dP^T : both operands K-major (d)
   constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
@@ -335,7 +339,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_wait(bar_kv, 0);
     issue_st(0);
   }
-  const int kk = k0 + tid;  // this thread's key row
+  const int kk = k0 + row_t;  // this thread's key row
   const bool k_in = kk < S;
   const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
   const float sc2 = p.scale * LOG2E;
@@ -348,7 +352,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_wait(bar_1, ph);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < AT_M / 32; ++c) {
+    for (int c = wg * 2; c < wg * 2 + 2; ++c) {
       uint32_t rs[32], rd[32];
       tmem_ld_32x32(tST + lane_off + c * 32, rs);
       tmem_ld_32x32(tdPT + lane_off + c * 32, rd);
@@ -380,7 +384,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint32_t off = (uint32_t)(c >> 1) * 16384 + sw128_offset(tid, (uint32_t)((c & 1) * 4 + g));
+        const uint32_t off = (uint32_t)(c >> 1) * 16384 + sw128_offset(row_t, (uint32_t)((c & 1) * 4 + g));
         *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
         *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
       }
@@ -409,9 +413,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tc_fence_after();
     if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
     {  // dQ partial: lanes are query rows here
-      const int q = q0 + tid;
-#pragma unroll
-      for (int c = 0; c < AT_D / 32; ++c) {
+      const int q = q0 + row_t;
+      {
+        const int c = wg;
         uint32_t r[32];
         tmem_ld_32x32(tdQ + lane_off + c * 32, r);
         tmem_wait_ld();
@@ -434,8 +438,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
     const uint32_t t = which == 0 ? tdK : tdV;
-#pragma unroll
-    for (int c = 0; c < AT_D / 32; ++c) {
+    {
+      const int c = wg;
       uint32_t r[32];
       tmem_ld_32x32(t + lane_off + c * 32, r);
       tmem_wait_ld();
@@ -673,8 +677,8 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
     attr = true;
   }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  if (a->valid) attn_bwd_kernel<true><<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
-  else attn_bwd_kernel<false><<<grid, 128, BWD_SMEM, stream>>>(tm, tdo, p);
+  if (a->valid) attn_bwd_kernel<true><<<grid, 256, BWD_SMEM, stream>>>(tm, tdo, p);
+  else attn_bwd_kernel<false><<<grid, 256, BWD_SMEM, stream>>>(tm, tdo, p);
   MB_CHECK_LAUNCH();
   {
     const long long n = tokens * (H / 8);

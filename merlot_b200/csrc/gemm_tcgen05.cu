@@ -34,13 +34,14 @@ struct GemmDev {
   uint32_t drop_thresh16; float drop_scale; uint64_t seed; uint32_t site;
 };
 
-template <int BN, bool TS>
+template <int BN, int EPI>
 struct GemmCfg {
+  static constexpr bool TS = EPI != 0;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (SMEM_LIMIT - (TS ? STAGING_BYTES : 0)) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (256 or 512: power of two)
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator stages, power-of-two allocation
   static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + (TS ? STAGING_BYTES : 0) + 1024 + 256;
 };
 
@@ -154,11 +155,12 @@ __device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int 
 
 // TS = true: bf16 outputs leave through 128B-swizzled smem staging boxes and TMA stores (fully coalesced, edge clipping
 // by the tensor map).  TS = false: direct register->global stores (fp32 outputs / atomics).
-template <int BN, bool A_MN, bool B_MN, bool TS>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_o1, const __grid_constant__ CUtensorMap tma_o2, const GemmDev p) {
-  using Cfg = GemmCfg<BN, TS>;
+  using Cfg = GemmCfg<BN, EPI>;
+  constexpr bool TS = EPI != 0;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte alignment
@@ -314,6 +316,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      } else if (EPI == 2) {
+        // fp32 accumulate-into-global (split-K wgrad): phases of 128 accumulator columns = 4 boxes of [128 rows][32 fp32],
+        // each left to one TMA reduce-add (coalesced red.add in the L2, no per-thread strided atomics).
+        constexpr int PH = (BN + 127) / 128;
+        for (int ph = 0; ph < PH; ++ph) {
+          if (issuer) tma_store_wait_read_all();
+          named_bar_sync(1, 32 * EPI_WARPS);
+          const int pcols = min(128, BN - ph * 128);         // accumulator columns in this phase
+          const int wcols = pcols / 2;                       // per warp-half: 64 or 32
+#pragma unroll 1
+          for (int c = 0; c < wcols / 32; ++c) {
+            uint32_t r[32];
+            const int pcol = half * wcols + c * 32;           // column inside the phase
+            tmem_ld_32x32(taddr + ph * 128 + pcol, r);
+            tmem_wait_ld();
+            uint8_t* box = staging + (pcol >> 5) * 16384;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)g)) =
+                  make_uint4(__float_as_uint(__uint_as_float(r[g * 4 + 0]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 1]) * p.alpha),
+                             __float_as_uint(__uint_as_float(r[g * 4 + 2]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 3]) * p.alpha));
+          }
+          if (ph == PH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 32 * EPI_WARPS);
+          if (issuer) {
+            const int c0 = n_blk * BN + ph * 128;
+            for (int b = 0; b < pcols / 32; ++b)
+              if (c0 + b * 32 < p.N) tma_reduce_add_2d(&tma_o1, staging + b * 16384, c0 + b * 32, m_blk * BLOCK_M);
+            tma_store_commit();
+          }
+        }
       } else {
         // single output: one phase, warp owns BN/2 columns -> boxes [half*BN/128 ...]; dual output (pre + act): BN/128
         // phases of 128 accumulator columns, warp owns 64 of them -> pre box `half`, act box `2+half`.
@@ -330,7 +368,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tmem_ld_32x32(taddr + tcol, r);
             tmem_wait_ld();
             const int col0 = n_blk * BN + tcol;
-            const int box = dual ? half : (half * (BN / 128) + (c >> 1));
+            const int box = dual ? half : (tcol >> 6);
             uint8_t* b1 = staging + box * 16384;
             uint8_t* b2 = staging + (2 + half) * 16384;
 #pragma unroll
@@ -340,7 +378,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
               if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
-              const int chunk16 = (c & 1) * 4 + g;
+              const int chunk16 = ((tcol & 63) >> 3) + g;
               if (dual) {
                 stage_bf16x8(b1, row_in_tile, chunk16, pre);
                 stage_bf16x8(b2, row_in_tile, chunk16, v);
@@ -394,11 +432,11 @@ struct ProfRec { cudaEvent_t e0, e1; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
-template <int BN, bool A_MN, bool B_MN, bool TS>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1, const CUtensorMap& to2,
                             const GemmDev& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, TS>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, TS>;
+  using Cfg = GemmCfg<BN, EPI>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
@@ -475,16 +513,19 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   int bn = g->block_n;
   if (bn == 0 && (g->flags & MERLOT_GEMM_ATOMIC)) bn = 256;  // wgrad: split-K fills the machine, wide tiles halve smem traffic
   if (bn == 0) {
+    const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
     double best = -1;
-    for (int cand : {256, 128}) {
+    for (int cand : {256, 192, 128}) {
+      if (dual && cand == 192) continue;  // pre+act staging works in 128-column phases
       long long tiles = (long long)p.m_blocks * ceil_div(g->N, cand);
       long long waves = ceil_div_ll(tiles, sms);
       double useful = (double)g->N / (double)(ceil_div(g->N, cand) * cand);
-      double eff = (double)tiles / (double)(waves * sms) * useful * (cand == 256 ? 1.0 : 0.80);
+      double eff = (double)tiles / (double)(waves * sms) * useful * (cand == 256 ? 1.0 : (cand == 192 ? 0.97 : 0.80));
       if (eff > best + 1e-9) { best = eff; bn = cand; }
     }
   }
-  MB_REQUIRE(bn == 128 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128 or 256 (got %d)", bn);
+  MB_REQUIRE(bn == 128 || bn == 192 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128, 192 or 256 (got %d)", bn);
+  MB_REQUIRE(!(bn == 192 && (g->flags & MERLOT_GEMM_GELU) && g->out2), MERLOT_EINVAL, "gemm: block_n 192 cannot be used with a dual (pre+act) output");
   p.n_blocks = ceil_div(g->N, bn);
   // ---- split-K (wgrad): fill the machine when the MN tile count is small ----
   int splits = g->splits;
@@ -519,12 +560,15 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   const long long tiles = (long long)mn_tiles * p.splits;
   const int grid = (int)(tiles < sms ? tiles : sms);
 
-  // bf16 outputs leave through TMA stores (swizzled smem staging); fp32 outputs / atomics use direct stores
-  const bool ts = !out_f32;
+  // epilogue route: 1 = bf16 tiles through swizzled smem staging + TMA store; 2 = fp32 split-K accumulation through TMA
+  // reduce-add (plain alpha*acc only); 0 = direct register->global stores (other fp32 outputs)
+  const bool plain = !g->bias && !g->resid && !(g->flags & (MERLOT_GEMM_GELU | MERLOT_GEMM_MUL_DGELU | MERLOT_GEMM_DROPOUT));
+  const int epi = !out_f32 ? 1
+                  : ((g->flags & MERLOT_GEMM_ATOMIC) && plain && (g->ld_out % 4) == 0 && ((uintptr_t)g->out % 16) == 0) ? 2 : 0;
   CUtensorMap to1, to2;
   memset(&to1, 0, sizeof(to1));
   memset(&to2, 0, sizeof(to2));
-  if (ts) {
+  if (epi == 1) {
     const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
     if (dual) MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
     rc = make_tmap_bf16_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 64, BLOCK_M);
@@ -532,16 +576,21 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
     rc = make_tmap_bf16_2d(&to2, dual ? g->out2 : g->out, (uint64_t)g->N, (uint64_t)g->M,
                            (uint64_t)(dual ? g->ld_out2 : g->ld_out), 64, BLOCK_M);
     if (rc) return rc;
+  } else if (epi == 2) {
+    rc = make_tmap_f32_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 32, BLOCK_M);
+    if (rc) return rc;
   }
-#define MB_GEMM_DISPATCH2(BN_, TS_)                                                                                  \
-  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true, TS_>(ta, tb, to1, to2, p, grid, stream);   \
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true, TS_>(ta, tb, to1, to2, p, grid, stream); \
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false, TS_>(ta, tb, to1, to2, p, grid, stream); \
-  return launch_gemm_inst<BN_, true, false, TS_>(ta, tb, to1, to2, p, grid, stream);
-#define MB_GEMM_DISPATCH(BN_)             \
-  if (ts) { MB_GEMM_DISPATCH2(BN_, true) } \
-  MB_GEMM_DISPATCH2(BN_, false)
+#define MB_GEMM_DISPATCH2(BN_, EPI_)                                                                                  \
+  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true, EPI_>(ta, tb, to1, to2, p, grid, stream);   \
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true, EPI_>(ta, tb, to1, to2, p, grid, stream); \
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false, EPI_>(ta, tb, to1, to2, p, grid, stream); \
+  return launch_gemm_inst<BN_, true, false, EPI_>(ta, tb, to1, to2, p, grid, stream);
+#define MB_GEMM_DISPATCH(BN_)                  \
+  if (epi == 1) { MB_GEMM_DISPATCH2(BN_, 1) }  \
+  if (epi == 2) { MB_GEMM_DISPATCH2(BN_, 2) }  \
+  MB_GEMM_DISPATCH2(BN_, 0)
   if (bn == 256) { MB_GEMM_DISPATCH(256) }
+  if (bn == 192) { MB_GEMM_DISPATCH(192) }
   MB_GEMM_DISPATCH(128)
 #undef MB_GEMM_DISPATCH
 #undef MB_GEMM_DISPATCH2

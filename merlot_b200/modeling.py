@@ -525,8 +525,8 @@ class MerlotModel(object):
         # tied embedding: dE += dlogits^T hn ; d_hn = dlogits E
         ops.gemm(dlog, h["hn"], a_mn_major=True, b_mn_major=True, out=st.G("word_embeddings/word_embeddings"), atomic=True,
                  M=V, N=H, K=nm)
-        d_hn = bf.get("mlm.d_hn", (nm, H), torch.float32)
-        ops.gemm(dlog, st.W("word_embeddings/word_embeddings"), b_mn_major=True, out=d_hn, M=nm, N=H, K=V)
+        d_hn = bf.get("mlm.d_hn", (nm, H), torch.float32, zero=True)  # split-K over the 50370-long contraction
+        ops.gemm(dlog, st.W("word_embeddings/word_embeddings"), b_mn_major=True, out=d_hn, atomic=True, M=nm, N=H, K=V)
         d_pooled = self._mlp_ln_bwd(h["proj"], d_hn) if h["proj"] else d_hn
         ops.scatter_add_rows(d_pooled, h["rows"], d_yj)
 

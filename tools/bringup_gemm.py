@@ -37,7 +37,7 @@ def run_major(a_mn, b_mn):
     g = torch.Generator(device="cpu").manual_seed(0)
     for (M, N, K, bn) in [(128, 256, 64, 256), (128, 128, 64, 128), (128, 256, 256, 256), (256, 512, 768, 256),
                           (200, 264, 136, 0), (8512, 768, 768, 0), (1024, 2304, 768, 0), (300, 50376, 768, 0),
-                          (3168, 3072, 768, 128), (1000, 768, 3072, 0)]:
+                          (3168, 3072, 768, 128), (1000, 768, 3072, 0), (520, 768, 768, 192), (8512, 2304, 768, 192)]:
         a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.5).bfloat16().to(dev)
         b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.5).bfloat16().to(dev)
         if (M % 8 and a_mn) or (N % 8 and b_mn):
@@ -96,10 +96,10 @@ def run_perf():
     g = torch.Generator(device="cpu").manual_seed(2)
     for (M, N, K, a_mn, b_mn, f32) in [(8512, 2304, 768, 0, 1, 0), (8512, 768, 768, 0, 1, 0), (8512, 3072, 768, 0, 1, 0),
                                        (8512, 768, 3072, 0, 1, 0), (768, 3072, 8512, 1, 1, 1), (3072, 768, 8512, 1, 1, 1),
-                                       (8192, 8192, 8192, 0, 0, 0)]:
+                                       (3168, 768, 768, 0, 1, 0), (3168, 2304, 768, 0, 1, 0), (768, 768, 8512, 1, 1, 1), (8192, 8192, 8192, 0, 0, 0)]:
         a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.1).bfloat16().to(dev)
         b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.1).bfloat16().to(dev)
-        for bn in (128, 256):
+        for bn in (128, 192, 256):
             out = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
             kw = dict(a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), out=out, atomic=bool(f32), block_n=bn)
             for _ in range(3):
