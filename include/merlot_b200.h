@@ -145,6 +145,14 @@ typedef struct merlot_ln_bwd {
 size_t merlot_layernorm_bwd_workspace_bytes(int H);
 int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream);
 
+/* Fused bf16 LayerNorm backward used inside the stacks (H % 8 == 0, H <= 1024, contiguous rows):
+ *   dx = LN'(dy) + dres;  dmask = dropout_bwd(dx) (when dropout_p > 0);  dbias += colsum(dmask or dx) (when dbias != NULL);
+ *   dgamma, dbeta accumulated.  dbias is the bias gradient of the tf.layers.dense whose output fed this residual add
+ *   (utils/transformer.py:136,162), i.e. it replaces one merlot_dropout_apply + one merlot_bias_grad pass. */
+int merlot_layernorm_bwd_fused(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                               const void* dres, void* dx, void* dmask, float* dgamma, float* dbeta, float* dbias,
+                               void* workspace, long long rows, int H, float dropout_p, uint64_t seed, uint32_t site,
+                               void* stream);
 /* bias gradient of a tf.layers.dense: out[n] += sum_m dy[m,n], optionally through the forward dropout mask */
 int merlot_bias_grad(const void* dy, int dy_f32, int ld, long long rows, int N, float* out, float dropout_p,
                      uint64_t seed, uint32_t site, void* stream);

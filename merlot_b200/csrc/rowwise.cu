@@ -201,6 +201,136 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
   for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * H + i] = sred[i];
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Fused bf16 LayerNorm backward for the transformer stacks.  One pass over (dy, x, dres) produces
+//   dx = LN'(dy) + dres                                   (the residual-stream gradient)
+//   dmask = dropout_bwd(dx)   (optional)                  (A operand of the next dgrad/wgrad GEMMs)
+//   partial[block] = { sum dy*xhat, sum dy, sum dmask }   (dgamma, dbeta, and the bias gradient of the next linear)
+// x and dy stay packed (bf16x2) in registers between the two sweeps so 2 blocks of 8 warps fit per SM.
+// -----------------------------------------------------------------------------------------------------------------
+template <int NCH>  // 16-byte chunks per lane: NCH = ceil(H / 256), H % 8 == 0 (H = 768 -> NCH = 3)
+__global__ void __launch_bounds__(128, 3)
+ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
+                    bf16* __restrict__ dx, bf16* __restrict__ dmask, float* __restrict__ partial, long long rows, int H, int want_bias,
+                    uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
+  extern __shared__ float sred[];  // [3][H]
+  const int nchunk = H >> 3;
+  const float invH = 1.0f / (float)H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float dg[NCH][8], db[NCH][8], bs[NCH][8];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dg[j][i] = 0.f; db[j][i] = 0.f; bs[j][i] = 0.f; }
+  for (long long row = (long long)blockIdx.x * nwarp + warp; row < rows; row += (long long)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    uint4 xp[NCH], dp[NCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      if (lane + 32 * j < nchunk) {
+        xp[j] = *reinterpret_cast<const uint4*>(x + (size_t)row * H + c);
+        dp[j] = *reinterpret_cast<const uint4*>(dy + (size_t)row * H + c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      if (lane + 32 * j >= nchunk) continue;
+      float g[8];
+      Vec8<float>::load(gamma + c, g);
+      const uint32_t* xu = reinterpret_cast<const uint32_t*>(&xp[j]);
+      const uint32_t* du = reinterpret_cast<const uint32_t*>(&dp[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xv = unpack_bf16x2(xu[i]), dv = unpack_bf16x2(du[i]);
+        const float xh0 = (xv.x - mu) * rs, xh1 = (xv.y - mu) * rs;
+        const float gd0 = g[2 * i] * dv.x, gd1 = g[2 * i + 1] * dv.y;
+        s1 += gd0 + gd1;
+        s2 += gd0 * xh0 + gd1 * xh1;
+        dg[j][2 * i] += dv.x * xh0; dg[j][2 * i + 1] += dv.y * xh1;
+        db[j][2 * i] += dv.x; db[j][2 * i + 1] += dv.y;
+      }
+    }
+    s1 = warp_sum(s1) * invH;
+    s2 = warp_sum(s2) * invH;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      if (lane + 32 * j >= nchunk) continue;
+      float g[8], o[8];
+      Vec8<float>::load(gamma + c, g);
+      const uint32_t* xu = reinterpret_cast<const uint32_t*>(&xp[j]);
+      const uint32_t* du = reinterpret_cast<const uint32_t*>(&dp[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xv = unpack_bf16x2(xu[i]), dv = unpack_bf16x2(du[i]);
+        o[2 * i] = rs * (g[2 * i] * dv.x - s1 - (xv.x - mu) * rs * s2);
+        o[2 * i + 1] = rs * (g[2 * i + 1] * dv.y - s1 - (xv.y - mu) * rs * s2);
+      }
+      if (dres != nullptr) {
+        float r[8];
+        Vec8<bf16>::load(dres + (size_t)row * H + c, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += r[i];
+      }
+      Vec8<bf16>::store(dx + (size_t)row * H + c, o);
+      if (want_bias) {
+        // the GEMMs consume the bf16-rounded gradient: sum exactly what they will read
+        uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        const uint32_t* pu = reinterpret_cast<const uint32_t*>(&pk);
+        float q[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(pu[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
+        if (drop_thresh16) {
+          const uint64_t lin = (uint64_t)row * (uint64_t)H + (uint64_t)c;
+          const uint32_t keep = dropout_keep8(seed, site, lin >> 3, drop_thresh16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) q[i] = ((keep >> i) & 1u) ? q[i] * drop_scale : 0.f;
+          uint4 mk = make_uint4(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]), pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
+          *reinterpret_cast<uint4*>(dmask + (size_t)row * H + c) = mk;
+          const uint32_t* mu2 = reinterpret_cast<const uint32_t*>(&mk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(mu2[i]); q[2 * i] = f.x; q[2 * i + 1] = f.y; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bs[j][i] += q[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int c = (lane + 32 * j) * 8;
+    if (lane + 32 * j >= nchunk) continue;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sred[c + i], dg[j][i]);
+      atomicAdd(&sred[H + c + i], db[j][i]);
+      if (want_bias) atomicAdd(&sred[2 * H + c + i], bs[j][i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) partial[(size_t)blockIdx.x * 3 * H + i] = sred[i];
+}
+
+// out_k[c] += sum_b partial[b][k*H + c] for k = 0..2 (dgamma, dbeta, bias); grid = (ceil(3H/256), RSPLIT2)
+constexpr int RSPLIT2 = 16;
+__global__ void reduce_partials3_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ o0,
+                                        float* __restrict__ o1, float* __restrict__ o2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = 3 * H;
+  if (c >= n) return;
+  float* dst = c < H ? o0 + c : (c < 2 * H ? o1 + (c - H) : (o2 ? o2 + (c - 2 * H) : nullptr));
+  if (!dst) return;
+  float s = 0.f;
+  for (int b = blockIdx.y; b < nblocks; b += RSPLIT2) s += partial[(size_t)b * n + c];
+  atomicAdd(dst, s);
+}
+
 // out[c] += sum_b partial[b][c]   (c in [0, n)); used for LN dgamma/dbeta.  grid = (ceil(n/256), RSPLIT): each thread sums
 // every RSPLIT-th partial row, then one fp32 atomic per thread.
 constexpr int RSPLIT = 16;
@@ -457,7 +587,7 @@ extern "C" int merlot_layernorm_fwd(const merlot_ln_t* d, void* stream_) {
   return MERLOT_OK;
 }
 
-extern "C" size_t merlot_layernorm_bwd_workspace_bytes(int H) { return (size_t)4 * 148 * 2 * (size_t)H * sizeof(float); }
+extern "C" size_t merlot_layernorm_bwd_workspace_bytes(int H) { return (size_t)4 * 148 * 3 * (size_t)H * sizeof(float); }
 
 extern "C" int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
@@ -484,6 +614,32 @@ extern "C" int merlot_layernorm_bwd(const merlot_ln_bwd_t* d, void* stream_) {
 #undef LNB
   MB_CHECK_LAUNCH();
   reduce_partials_kernel<<<dim3(ceil_div(2 * d->H, 256), RSPLIT), 256, 0, st>>>(part, grid, 2 * d->H, d->dgamma, d->dbeta, d->H);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_layernorm_bwd_fused(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                                          const void* dres, void* dx, void* dmask, float* dgamma, float* dbeta, float* dbias,
+                                          void* workspace, long long rows, int H, float dropout_p, uint64_t seed, uint32_t site,
+                                          void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, MERLOT_EINVAL, "layernorm_bwd_fused: null pointer");
+  MB_REQUIRE(H % 8 == 0 && H > 0 && H <= 1024, MERLOT_ESHAPE, "layernorm_bwd_fused: H must be a multiple of 8, <= 1024 (got %d)", H);
+  MB_REQUIRE(dropout_p <= 0.f || (dmask && dbias), MERLOT_EINVAL, "layernorm_bwd_fused: dropout needs dmask and dbias");
+  if (rows == 0) return MERLOT_OK;
+  const uint32_t th = dropout_p > 0.f ? thresh16(dropout_p) : 0;
+  const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  long long want = ceil_div_ll(rows, 4);
+  const int grid = (int)(want < 3 * 148 ? want : 3 * 148);
+  const size_t smem = (size_t)3 * H * sizeof(float);
+  float* part = reinterpret_cast<float*>(workspace);
+#define LNF(N_)                                                                                                            \
+  ln_bwd_fused_kernel<N_><<<grid, 128, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)dres, \
+                                                   (bf16*)dx, (bf16*)dmask, part, rows, H, dbias != nullptr, th, sc, seed, site)
+  if (H <= 256) LNF(1); else if (H <= 512) LNF(2); else if (H <= 768) LNF(3); else LNF(4);
+#undef LNF
+  MB_CHECK_LAUNCH();
+  reduce_partials3_kernel<<<dim3(ceil_div(3 * H, 256), RSPLIT2), 256, 0, st>>>(part, grid, H, dgamma, dbeta, dbias);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }

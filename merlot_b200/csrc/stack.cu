@@ -59,15 +59,6 @@ static int ln_fwd(const void* x, void* y, const float* g, const float* b, float*
   return merlot_layernorm_fwd(&d, st);
 }
 
-static int ln_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const void* dres,
-                  void* dx, float* dgamma, float* dbeta, void* ws, long long rows, int H, cudaStream_t st) {
-  merlot_ln_bwd_t d;
-  memset(&d, 0, sizeof(d));
-  d.dy = dy; d.ld_dy = H; d.x = x; d.ld_x = H; d.mean = mean; d.rstd = rstd; d.gamma = gamma; d.dres = dres; d.ld_dres = H;
-  d.dx = dx; d.ld_dx = H; d.dgamma = dgamma; d.dbeta = dbeta; d.workspace = ws; d.rows = rows; d.H = H;
-  return merlot_layernorm_bwd(&d, st);
-}
-
 static merlot_gemm_t gemm_base(int M, int N, int K) {
   merlot_gemm_t g;
   memset(&g, 0, sizeof(g));
@@ -215,23 +206,28 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
   MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)M * H * 4, st));
 
   const bool drop = s->hidden_dropout_p > 0.f;
+  // ln_bwd(dy, x, stats, gamma, dres) -> dx [+ dropout-masked copy + bias gradient of the linear layer that fed this
+  // residual add]; `next_bias`/`next_site` describe that layer (nullptr: nobody consumes a masked copy)
+  auto ln_bwd_f = [&](const void* dy_, const void* x_, const float* mean_, const float* rstd_, const float* gamma_, const void* dres_,
+                      void* dx_, float* dgamma_, float* dbeta_, float* next_bias, uint32_t next_site) -> int {
+    return merlot_layernorm_bwd_fused(dy_, x_, mean_, rstd_, gamma_, dres_, dx_, (drop && next_bias) ? dmask : nullptr, dgamma_,
+                                      dbeta_, next_bias, lnws, M, H, (drop && next_bias) ? s->hidden_dropout_p : 0.f,
+                                      s->dropout_seed, next_site, st);
+  };
   char* dh = dhA;
   char* dh_other = dhB;
-  {  // final LN
+  {  // final LN; its output is the gradient of the last layer's FFN2 output
     LayerAct A = carve(s, arena + per * (s->layers - 1));
-    RC(ln_bwd(s->dy, A.hout, mean_f, rstd_f, s->final_gamma, nullptr, dh, s->d_final_gamma, s->d_final_beta, lnws, M, H, st));
+    const merlot_layer_params_t& PL = s->layer_params[s->layers - 1];
+    RC(ln_bwd_f(s->dy, A.hout, mean_f, rstd_f, s->final_gamma, nullptr, dh, s->d_final_gamma, s->d_final_beta, PL.g_b_2,
+                s->dropout_site_base + 2 * (s->layers - 1) + 1));
   }
   for (int l = s->layers - 1; l >= 0; --l) {
     const merlot_layer_params_t& P = s->layer_params[l];
     LayerAct A = carve(s, arena + per * l);
     const void* h_in = (l == 0) ? s->h_in : (const void*)carve(s, arena + per * (l - 1)).hout;
-    // ---- FFN2: hout = hmid + drop(act W2 + b2) ----
-    const void* d = dh;
-    if (drop) {
-      RC(merlot_dropout_apply(dh, H, dmask, H, M, H, s->hidden_dropout_p, s->dropout_seed, s->dropout_site_base + 2 * l + 1, st));
-      d = dmask;
-    }
-    RC(merlot_bias_grad(d, 0, H, M, H, P.g_b_2, 0.f, 0, 0, st));
+    // ---- FFN2: hout = hmid + drop(act W2 + b2);  d = dropout_bwd(dh) and db2 were produced by the LN backward above ----
+    const void* d = drop ? (const void*)dmask : (const void*)dh;
     RC(linear_wgrad(A.act, I, d, H, P.g_w_2, M, st));
     {
       merlot_gemm_t e = gemm_base(0, 0, 0);
@@ -242,16 +238,12 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
     RC(merlot_bias_grad(dpre, 0, I, M, I, P.g_b_1, 0.f, 0, 0, st));
     RC(linear_wgrad(A.x2, H, dpre, I, P.g_w_1, M, st));
     RC(linear_dgrad(dpre, I, P.w_1, H, dtmp, M, gemm_base(0, 0, 0), st));
-    // ---- LN2: d_hmid = dh + LN'(dx2) ----
-    RC(ln_bwd(dtmp, A.hmid, A.mean2, A.rstd2, P.ln2_gamma, dh, dh_other, P.g_ln2_gamma, P.g_ln2_beta, lnws, M, H, st));
+    // ---- LN2: d_hmid = dh + LN'(dx2); also emits dropout_bwd(d_hmid) and db_o for the out-projection ----
+    RC(ln_bwd_f(dtmp, A.hmid, A.mean2, A.rstd2, P.ln2_gamma, dh, dh_other, P.g_ln2_gamma, P.g_ln2_beta, P.g_b_o,
+                s->dropout_site_base + 2 * l));
     { char* t = dh; dh = dh_other; dh_other = t; }
     // ---- attention output projection: hmid = h + drop(ctx Wo + bo) ----
-    d = dh;
-    if (drop) {
-      RC(merlot_dropout_apply(dh, H, dmask, H, M, H, s->hidden_dropout_p, s->dropout_seed, s->dropout_site_base + 2 * l, st));
-      d = dmask;
-    }
-    RC(merlot_bias_grad(d, 0, H, M, H, P.g_b_o, 0.f, 0, 0, st));
+    d = drop ? (const void*)dmask : (const void*)dh;
     RC(linear_wgrad(A.ctx, H, d, H, P.g_w_o, M, st));
     RC(linear_dgrad(d, H, P.w_o, H, dtmp, M, gemm_base(0, 0, 0), st));  // d_ctx
     // ---- attention ----
@@ -267,9 +259,11 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
     RC(merlot_bias_grad(dqkv, 0, 3 * H, M, 3 * H, P.g_b_qkv, 0.f, 0, 0, st));
     RC(linear_wgrad(A.x1, H, dqkv, 3 * H, P.g_w_qkv, M, st));
     RC(linear_dgrad(dqkv, 3 * H, P.w_qkv, H, dtmp, M, gemm_base(0, 0, 0), st));
-    // ---- LN1: d_h_in = d_hmid + LN'(dx1) ----
+    // ---- LN1: d_h_in = d_hmid + LN'(dx1); feeds the previous layer's FFN2 ----
     void* dst = (l == 0 && s->dh_in) ? s->dh_in : (void*)dh_other;
-    RC(ln_bwd(dtmp, h_in, A.mean1, A.rstd1, P.ln1_gamma, dh, dst, P.g_ln1_gamma, P.g_ln1_beta, lnws, M, H, st));
+    float* nb = (l > 0) ? s->layer_params[l - 1].g_b_2 : nullptr;
+    RC(ln_bwd_f(dtmp, h_in, A.mean1, A.rstd1, P.ln1_gamma, dh, dst, P.g_ln1_gamma, P.g_ln1_beta, nb,
+                l > 0 ? s->dropout_site_base + 2 * (l - 1) + 1 : 0));
     { char* t = dh; dh = dh_other; dh_other = t; }
   }
   return MERLOT_OK;
