@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
+  pdl_launch_dependents();
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
   const int n_kv = (S + AT_N - 1) / AT_N;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  pdl_wait();
   if (HAS_MASK) {  // key validity of this batch element as a bitmask (bit k%32 of word k/32)
     for (int k = tid; k < n_kv * AT_N; k += 128) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
@@ -275,6 +277,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every tile's columns
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3, row_t = quad * 32 + lane;
+  pdl_launch_dependents();
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
@@ -286,6 +289,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  pdl_wait();
   if (HAS_MASK) {
     for (int k = tid; k < n_q * AT_M; k += 256) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
@@ -464,6 +468,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 // D[b,h,q] = sum_d dO[q,hd] * O[q,hd]   (one warp per (token, head) pair would waste lanes; 8 lanes x 8 elems per head)
 __global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, int ld, float* __restrict__ dsum,
                                  int B, int S, int heads) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long item = gid >> 3;  // (token, head)
   const int sub = (int)(gid & 7);
@@ -497,6 +503,8 @@ __global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restr
 // dq fp32 accumulator -> bf16 q-block of dqkv, and re-zero the accumulator for the next layer
 __global__ void attn_dq_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv, long long rows,
                                       int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = H / 8;
   if (gid >= rows * per_row) return;
@@ -534,7 +542,9 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
     mbar_init(bar_k, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
     fence_barrier_init();
   }
+  pdl_launch_dependents();
   if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -640,8 +650,8 @@ extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
     attr = true;
   }
   dim3 grid(ceil_div(a->S, AT_M), a->heads, a->B);
-  if (a->valid) attn_fwd_kernel<true><<<grid, 128, FWD_SMEM, stream>>>(tm, p);
-  else attn_fwd_kernel<false><<<grid, 128, FWD_SMEM, stream>>>(tm, p);
+  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), FWD_SMEM, stream, tm, p));
+  else MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), FWD_SMEM, stream, tm, p));
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
@@ -659,9 +669,9 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
   const long long tokens = (long long)a->B * a->S;
   {  // D = rowsum(dO * O)
     const long long threads = tokens * a->heads * 8;
-    attn_dsum_kernel<<<(unsigned)ceil_div_ll(threads, 256), 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(a->ctx), reinterpret_cast<const bf16*>(a->d_ctx), a->ld_ctx,
-        a->dsum, a->B, a->S, a->heads);
+    MB_CHECK_CUDA(launch_pdl(attn_dsum_kernel, dim3((unsigned)ceil_div_ll(threads, 256)), dim3(256), 0, stream,
+                             reinterpret_cast<const bf16*>(a->ctx), reinterpret_cast<const bf16*>(a->d_ctx), a->ld_ctx, a->dsum,
+                             a->B, a->S, a->heads));
     MB_CHECK_LAUNCH();
   }
   CUtensorMap tm, tdo;
@@ -677,13 +687,13 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
     attr = true;
   }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  if (a->valid) attn_bwd_kernel<true><<<grid, 256, BWD_SMEM, stream>>>(tm, tdo, p);
-  else attn_bwd_kernel<false><<<grid, 256, BWD_SMEM, stream>>>(tm, tdo, p);
+  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), BWD_SMEM, stream, tm, tdo, p));
+  else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), BWD_SMEM, stream, tm, tdo, p));
   MB_CHECK_LAUNCH();
   {
     const long long n = tokens * (H / 8);
-    attn_dq_finish_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(a->dq_accum, a->ld_dq, p.dqkv, a->ld_dqkv,
-                                                                              tokens, H);
+    MB_CHECK_CUDA(launch_pdl(attn_dq_finish_kernel, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, stream, a->dq_accum,
+                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H));
     MB_CHECK_LAUNCH();
   }
   return MERLOT_OK;
@@ -701,7 +711,7 @@ extern "C" int merlot_attention_colsum(const merlot_attn_t* a, void* stream_) {
   static bool attr = false;
   if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM)); attr = true; }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  attn_colsum_kernel<<<grid, 128, CS_SMEM, stream>>>(tm, p);
+  MB_CHECK_CUDA(launch_pdl(attn_colsum_kernel, grid, dim3(128), CS_SMEM, stream, tm, p));
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }

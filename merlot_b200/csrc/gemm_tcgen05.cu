@@ -177,6 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -200,6 +201,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
 
@@ -449,7 +451,7 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
     rec.flops = 2.0 * (double)p.M * (double)p.N * (double)p.K;
     MB_CHECK_CUDA(cudaEventRecord(rec.e0, stream));
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_TOTAL, stream>>>(ta, tb, to1, to2, p);
+  MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_TOTAL, stream, ta, tb, to1, to2, p));
   MB_CHECK_LAUNCH();
   if (g_prof_on) {
     MB_CHECK_CUDA(cudaEventRecord(rec.e1, stream));

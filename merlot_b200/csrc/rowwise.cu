@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TI* __restrict__ x, i
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
                                                      int H, float eps, int map_per, int map_stride, int map_off,
                                                      uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -212,14 +214,17 @@ template <int NCH>  // 16-byte chunks per lane: NCH = ceil(H / 256), H % 8 == 0 
 __global__ void __launch_bounds__(128, 3)
 ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
-                    bf16* __restrict__ dx, bf16* __restrict__ dmask, float* __restrict__ partial, long long rows, int H, int want_bias,
+                    bf16* __restrict__ dx, bf16* __restrict__ dmask, float* __restrict__ out_g, float* __restrict__ out_b,
+                    float* __restrict__ out_bias, long long rows, int H, int want_bias,
                     uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
   extern __shared__ float sred[];  // [3][H]
+  pdl_launch_dependents();
   const int nchunk = H >> 3;
   const float invH = 1.0f / (float)H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
+  pdl_wait();
   float dg[NCH][8], db[NCH][8], bs[NCH][8];
 #pragma unroll
   for (int j = 0; j < NCH; ++j)
@@ -314,7 +319,11 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) partial[(size_t)blockIdx.x * 3 * H + i] = sred[i];
+  // block partials -> fp32 red.add straight into the gradient arena (dgamma | dbeta | bias)
+  for (int i = threadIdx.x; i < (want_bias ? 3 : 2) * H; i += blockDim.x) {
+    float* dst = i < H ? out_g + i : (i < 2 * H ? out_b + (i - H) : out_bias + (i - 2 * H));
+    atomicAdd(dst, sred[i]);
+  }
 }
 
 // out_k[c] += sum_b partial[b][k*H + c] for k = 0..2 (dgamma, dbeta, bias); grid = (ceil(3H/256), RSPLIT2)
@@ -351,6 +360,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int ld, long long rows, int N, float* __restrict__ out,
                                                      uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
   __shared__ float sred[8][256];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -575,13 +586,13 @@ extern "C" int merlot_layernorm_fwd(const merlot_ln_t* d, void* stream_) {
   const unsigned grid = (unsigned)ceil_div_ll(d->rows, 8);
 #define LN_ARGS d->ld_x, (d->y), d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site
   if (!d->x_f32 && !d->y_f32)
-    ln_fwd_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)d->x, d->ld_x, (bf16*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site);
+    MB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)d->x, d->ld_x, (bf16*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site));
   else if (d->x_f32 && !d->y_f32)
-    ln_fwd_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)d->x, d->ld_x, (bf16*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site);
+    MB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<float, bf16>, dim3(grid), dim3(256), 0, st, (const float*)d->x, d->ld_x, (bf16*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site));
   else if (d->x_f32 && d->y_f32)
-    ln_fwd_kernel<float, float><<<grid, 256, 0, st>>>((const float*)d->x, d->ld_x, (float*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site);
+    MB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<float, float>, dim3(grid), dim3(256), 0, st, (const float*)d->x, d->ld_x, (float*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site));
   else
-    ln_fwd_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)d->x, d->ld_x, (float*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site);
+    MB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<bf16, float>, dim3(grid), dim3(256), 0, st, (const bf16*)d->x, d->ld_x, (float*)d->y, d->ld_y, d->gamma, d->beta, d->mean, d->rstd, d->rows, d->H, d->eps, d->map_per, d->map_stride, d->map_off, th, sc, d->dropout_seed, d->dropout_site));
 #undef LN_ARGS
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
@@ -623,7 +634,7 @@ extern "C" int merlot_layernorm_bwd_fused(const void* dy, const void* x, const f
                                           void* workspace, long long rows, int H, float dropout_p, uint64_t seed, uint32_t site,
                                           void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  MB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, MERLOT_EINVAL, "layernorm_bwd_fused: null pointer");
+  MB_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, MERLOT_EINVAL, "layernorm_bwd_fused: null pointer");
   MB_REQUIRE(H % 8 == 0 && H > 0 && H <= 1024, MERLOT_ESHAPE, "layernorm_bwd_fused: H must be a multiple of 8, <= 1024 (got %d)", H);
   MB_REQUIRE(dropout_p <= 0.f || (dmask && dbias), MERLOT_EINVAL, "layernorm_bwd_fused: dropout needs dmask and dbias");
   if (rows == 0) return MERLOT_OK;
@@ -632,14 +643,13 @@ extern "C" int merlot_layernorm_bwd_fused(const void* dy, const void* x, const f
   long long want = ceil_div_ll(rows, 4);
   const int grid = (int)(want < 3 * 148 ? want : 3 * 148);
   const size_t smem = (size_t)3 * H * sizeof(float);
-  float* part = reinterpret_cast<float*>(workspace);
-#define LNF(N_)                                                                                                            \
-  ln_bwd_fused_kernel<N_><<<grid, 128, smem, st>>>((const bf16*)dy, (const bf16*)x, mean, rstd, gamma, (const bf16*)dres, \
-                                                   (bf16*)dx, (bf16*)dmask, part, rows, H, dbias != nullptr, th, sc, seed, site)
+  (void)workspace;
+#define LNF(N_)                                                                                                          \
+  MB_CHECK_CUDA(launch_pdl(ln_bwd_fused_kernel<N_>, dim3(grid), dim3(128), smem, st, (const bf16*)dy, (const bf16*)x, mean, rstd, \
+                           gamma, (const bf16*)dres, (bf16*)dx, (bf16*)dmask, dgamma, dbeta, dbias, rows, H,           \
+                           (int)(dbias != nullptr), th, sc, seed, site))
   if (H <= 256) LNF(1); else if (H <= 512) LNF(2); else if (H <= 768) LNF(3); else LNF(4);
 #undef LNF
-  MB_CHECK_LAUNCH();
-  reduce_partials3_kernel<<<dim3(ceil_div(3 * H, 256), RSPLIT2), 256, 0, st>>>(part, grid, H, dgamma, dbeta, dbias);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
@@ -655,8 +665,8 @@ extern "C" int merlot_bias_grad(const void* dy, int dy_f32, int ld, long long ro
   long long slabs = ceil_div_ll(rows, 64);
   if (slabs > 128) slabs = 128;
   dim3 grid(ceil_div(N, 256), (unsigned)slabs);
-  if (dy_f32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, ld, rows, N, out, th, sc, seed, site);
-  else colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, ld, rows, N, out, th, sc, seed, site);
+  if (dy_f32) MB_CHECK_CUDA(launch_pdl(colsum_kernel<float>, grid, dim3(256), 0, st, (const float*)dy, ld, rows, N, out, th, sc, seed, site));
+  else MB_CHECK_CUDA(launch_pdl(colsum_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)dy, ld, rows, N, out, th, sc, seed, site));
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
