@@ -70,7 +70,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                                        str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -263,14 +263,17 @@ def run_ours(args):
     roof = None
     if rank == 0:
         lib.merlot_gemm_profile_begin()
-        one_step(feats)
+    one_step(feats)  # every rank takes part (the step contains the NCCL collectives); only rank 0 records events
+    if rank == 0:
         tm, fl, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         L.check(lib.merlot_gemm_profile_end(ctypes.byref(tm), ctypes.byref(fl), ctypes.byref(nl)))
         sustained, burst, hbm, how = peaks()
         ach = fl.value / (tm.value * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (K1, tcgen05)", "achieved": ach, "peak": sustained,
                 "unit": "TFLOP/s", "frac": ach / sustained, "traffic": None, "peak_source": f"{how} bf16_tflops_sustained",
-                "launches_per_step": nl.value, "gemm_ms_per_step": tm.value, "gemm_share_of_step": tm.value / (ms_total / args.steps)}
+                "launches_per_step": nl.value, "gemm_ms_per_step": tm.value, "gemm_share_of_step": tm.value / (ms_total / args.steps),
+                "note": "sum over all K1 launches of one step: sum(2MNK) / sum(CUDA-event duration on the launch stream)"}
+    torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
 

@@ -729,9 +729,11 @@ class MerlotModel(object):
     # ---------------------------------------------------------------------------------------------------------
     # backward of the whole model: call after mask_loss / contrastive_loss / temporal_loss (whichever are in the loss)
     # ---------------------------------------------------------------------------------------------------------
-    def backward(self):
+    def backward(self, on_non_vit_grads_ready=None):
         """d(lang_loss + contr_loss + temp_loss)/d(params) accumulated into store.g  (model/modeling.py:713 loss,
-        utils/optimization.py:176 tf.gradients)."""
+        utils/optimization.py:176 tf.gradients).  Order: heads -> joint encoder -> language-only encoder -> (callback: every
+        gradient outside vision_backbone/vision_transformer is final; data-parallel training starts their all-reduce here)
+        -> ViT."""
         if not self._save:
             raise RuntimeError("MerlotModel was built without save_for_backward (is_training=False)")
         cfg, st, bf, D = self.config, self.store, self._bufs, self._dims
@@ -767,6 +769,17 @@ class MerlotModel(object):
         ops.group_rowsum(dxz, N, vcl, 0, 1, None, st.G("vision_backbone/final_pe/cls_emb"), H)
         ops.group_rowsum(dxz, N, vcl, 1, D["h2"] * D["w2"], self._grid_idxmap(D["h2"], D["w2"]),
                          st.G("vision_backbone/final_pe/pos_embs"), H)
+        # ---- language-only encoder ----
+        if self._mask_input:
+            Blo, Llo = self._ids_lo.shape
+            d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
+            ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
+            d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
+            self._lo.backward(d_ylo, d_h0lo)
+            self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
+                            Blo, Llo)
+        if on_non_vit_grads_ready is not None:
+            on_non_vit_grads_ready()
         # ---- ViT ----
         d_h0v = bf.get("bwd.d_h0v", (Mv, H), torch.bfloat16)
         self._vit.backward(d_hv, d_h0v)
@@ -781,16 +794,6 @@ class MerlotModel(object):
         ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
         ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
                  out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
-        # ---- language-only encoder ----
-        if self._mask_input:
-            Blo, Llo = self._ids_lo.shape
-            d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
-            ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
-            d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
-            self._lo.backward(d_ylo, d_h0lo)
-            self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
-                            Blo, Llo)
-
     def _embed_bwd(self, tag, norm_scope_name, ids_2d, dy, remap, dropout, groups, Lseq):
         st, bf = self.store, self._bufs
         H, R = self.hidden_size, ids_2d.numel()

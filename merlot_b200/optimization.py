@@ -55,12 +55,26 @@ class AdamOptimizer:
         return dict(beta1=float(b1), omb1=float(np.float32(1.0) - b1), beta2=float(b2), omb2=float(np.float32(1.0) - b2),
                     eps=float(np.float32(eps)), lr_t=float(lr_t), wd=float(np.float32(wd)), lr=float(np.float32(lr) * scale))
 
-    def apply_gradients(self, grad_scale: float = 1.0, skip: Iterable[str] = (), zero_grad=True):
+    def apply_gradients(self, grad_scale: float = 1.0, skip: Iterable[str] = (), zero_grad=True, only=None, advance=True):
         """One optimizer step on every parameter that received a gradient; `skip` lists parameters whose gradient is
-        None in the reference (optimization.py:343-344 leaves those untouched)."""
+        None in the reference (optimization.py:343-344 leaves those untouched).  `only` = [(a, b), ...] restricts the update
+        to those arena ranges (data-parallel training updates the already all-reduced part while the rest is in flight);
+        pass advance=False for all but the last partial call of a step."""
         st = self.store
         step = st.global_step
         skip_ranges = sorted((st.entries[n].offset, st.entries[n].offset + st.entries[n].padded) for n in skip)
+        if only is not None:  # complement of `only` is skipped in this call
+            cur, extra = 0, []
+            for a, b in sorted(only):
+                if a > cur:
+                    extra.append((cur, a))
+                cur = max(cur, b)
+            if cur < st.total:
+                extra.append((cur, st.total))
+            zero_ranges = [r for r in skip_ranges]
+            skip_ranges = sorted(skip_ranges + extra)
+        else:
+            zero_ranges = skip_ranges
         for hyper, off, cnt in st.groups:
             if hyper[0] == 0:  # learning_rate 0 => not trainable (:149-156)
                 continue
@@ -77,10 +91,11 @@ class AdamOptimizer:
             for a, b in segs:
                 ops.adamw_step(st.p[a:b], st.g[a:b], st.m[a:b], st.v[a:b], st.pb[a:b], b - a, s["beta1"], s["omb1"], s["beta2"],
                                s["omb2"], s["eps"], s["lr_t"], s["wd"], grad_scale, zero_grad)
-        if zero_grad and skip_ranges:
-            for a, b in skip_ranges:
+        if zero_grad and zero_ranges and advance:
+            for a, b in zero_ranges:
                 st.g[a:b].zero_()
-        st.global_step += 1  # :251-253
+        if advance:
+            st.global_step += 1  # :251-253
 
     def current_lr(self):
         return float(np.float32(self.learning_rate) * learning_rate_scale(self.store.global_step, self.num_train_steps,

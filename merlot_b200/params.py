@@ -158,6 +158,17 @@ class ParamStore:
                 self.entries[e.name] = e
             self.groups.append((hyper, start, off - start))
         self.total = off
+        # contiguous [ViT | everything else] split of every group: the non-ViT gradients are final before the ViT backward
+        # starts, so their all-reduce can overlap it (train.DataParallel)
+        self.vit_ranges, self.rest_ranges = [], []
+        for _, goff, gcnt in self.groups:
+            ends = [e.offset + e.padded for e in self.entries.values()
+                    if goff <= e.offset < goff + gcnt and e.name.startswith("vision_backbone/vision_transformer/")]
+            vend = max(ends) if ends else goff
+            if vend > goff:
+                self.vit_ranges.append((goff, vend))
+            if goff + gcnt > vend:
+                self.rest_ranges.append((vend, goff + gcnt))
         self.p = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.g = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.pb = torch.zeros(off, dtype=torch.bfloat16, device=self.device)

@@ -40,6 +40,18 @@ class DataParallel:
         if self.world > 1:
             self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM)
 
+    def all_reduce_ranges_async(self, g: torch.Tensor, ranges):
+        """Start summing g[a:b] for every range on the NCCL stream, ordered after the work already queued on the current
+        stream; returns handles for wait_all().  Lets the collective overlap the rest of the backward pass."""
+        if self.world <= 1:
+            return []
+        return [self.dist.all_reduce(g[a:b], op=self.dist.ReduceOp.SUM, async_op=True) for a, b in ranges if b > a]
+
+    @staticmethod
+    def wait_all(handles):
+        for h in handles:
+            h.wait()  # the current stream waits for the collective; no host sync
+
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
         out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         self.dist.all_gather_into_tensor(out, x.contiguous())
@@ -126,11 +138,20 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
         losses["learning_rate"] = optimizer.current_lr()
 
         def train_op():
-            model.backward()
             world = dist.world if dist is not None else 1
+            pending = []
             if world > 1:
-                dist.all_reduce_grads(store.g)
-            optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True)
+                # bucket 1 (everything outside the ViT) is all-reduced while the ViT backward runs; bucket 2 (ViT) is
+                # all-reduced while AdamW updates bucket 1
+                model.backward(on_non_vit_grads_ready=lambda: pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges)))
+                vit_pending = dist.all_reduce_ranges_async(store.g, store.vit_ranges)
+                dist.wait_all(pending)
+                optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=store.rest_ranges, advance=False)
+                dist.wait_all(vit_pending)
+                optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=store.vit_ranges, advance=True)
+            else:
+                model.backward()
+                optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True)
 
         return StepSpec(model, (lang_loss, contr_loss, temp_loss), losses, train_op)
 
