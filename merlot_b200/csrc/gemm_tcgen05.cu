@@ -18,7 +18,7 @@ constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom
 constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each owning half of the tile's columns
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int SMEM_LIMIT = 232448 - 1024 - 256;  // 227 KB minus alignment slack and barriers
-constexpr int STAGING_BYTES = 65536;             // 4 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
+constexpr int STAGING_BYTES = 32768;             // 2 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
 
 struct GemmDev {
   int M, N, K;
@@ -318,74 +318,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      } else if (EPI == 2) {
-        // fp32 accumulate-into-global (split-K wgrad): phases of 128 accumulator columns = 4 boxes of [128 rows][32 fp32],
-        // each left to one TMA reduce-add (coalesced red.add in the L2, no per-thread strided atomics).
-        constexpr int PH = (BN + 127) / 128;
-        for (int ph = 0; ph < PH; ++ph) {
-          if (issuer) tma_store_wait_read_all();
+      } else {
+        // Staged epilogue in phases of PCOLS accumulator columns; each phase fills the two 16 KB staging boxes
+        // ([128 rows][128 B], 128B-swizzled) and hands them to TMA:
+        //   bf16 single output : PCOLS = 128 -> box h = columns [64h, 64h+64) of the phase            (TMA store)
+        //   bf16 pre+act output: PCOLS = 64  -> box 0 = pre-activation, box 1 = gelu, same 64 columns  (2 TMA stores)
+        //   fp32 split-K accum : PCOLS = 64  -> box h = 32 fp32 columns                                (TMA reduce-add)
+        const int pcols_max = (EPI == 2 || dual) ? 64 : 128;
+        const int phases = (BN + pcols_max - 1) / pcols_max;
+        for (int ph = 0; ph < phases; ++ph) {
+          if (issuer) tma_store_wait_read_all();  // staging is free again
           named_bar_sync(1, 32 * EPI_WARPS);
-          const int pcols = min(128, BN - ph * 128);         // accumulator columns in this phase
-          const int wcols = pcols / 2;                       // per warp-half: 64 or 32
+          const int pcols = min(pcols_max, BN - ph * pcols_max);
+          const int wcols = pcols >> 1;           // columns per warp half: 64 or 32
+          const int tcol0 = ph * pcols_max + half * wcols;
 #pragma unroll 1
           for (int c = 0; c < wcols / 32; ++c) {
             uint32_t r[32];
-            const int pcol = half * wcols + c * 32;           // column inside the phase
-            tmem_ld_32x32(taddr + ph * 128 + pcol, r);
-            tmem_wait_ld();
-            uint8_t* box = staging + (pcol >> 5) * 16384;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)g)) =
-                  make_uint4(__float_as_uint(__uint_as_float(r[g * 4 + 0]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 1]) * p.alpha),
-                             __float_as_uint(__uint_as_float(r[g * 4 + 2]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 3]) * p.alpha));
-          }
-          if (ph == PH - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 32 * EPI_WARPS);
-          if (issuer) {
-            const int c0 = n_blk * BN + ph * 128;
-            for (int b = 0; b < pcols / 32; ++b)
-              if (c0 + b * 32 < p.N) tma_reduce_add_2d(&tma_o1, staging + b * 16384, c0 + b * 32, m_blk * BLOCK_M);
-            tma_store_commit();
-          }
-        }
-      } else {
-        // single output: one phase, warp owns BN/2 columns -> boxes [half*BN/128 ...]; dual output (pre + act): BN/128
-        // phases of 128 accumulator columns, warp owns 64 of them -> pre box `half`, act box `2+half`.
-        const int phases = dual ? BN / 128 : 1;
-        const int chunks = dual ? 2 : BN / 64;  // 32-column chunks per warp per phase
-        for (int ph = 0; ph < phases; ++ph) {
-          if (issuer) tma_store_wait_read_all();        // staging is free again
-          named_bar_sync(1, 32 * EPI_WARPS);
-          const int tcol_base = dual ? ph * 128 + half * 64 : half * (BN / 2);
-#pragma unroll 1
-          for (int c = 0; c < chunks; ++c) {
-            uint32_t r[32];
-            const int tcol = tcol_base + c * 32;
+            const int tcol = tcol0 + c * 32;
             tmem_ld_32x32(taddr + tcol, r);
             tmem_wait_ld();
             const int col0 = n_blk * BN + tcol;
-            const int box = dual ? half : (tcol >> 6);
-            uint8_t* b1 = staging + box * 16384;
-            uint8_t* b2 = staging + (2 + half) * 16384;
+            if (EPI == 2) {
+              uint8_t* box = staging + half * 16384;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              float v[8], pre[8];
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)g)) =
+                    make_uint4(__float_as_uint(__uint_as_float(r[g * 4 + 0]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 1]) * p.alpha),
+                               __float_as_uint(__uint_as_float(r[g * 4 + 2]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 3]) * p.alpha));
+            } else {
+              const int pcol = half * wcols + c * 32;  // column inside the phase
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
-              const int chunk16 = ((tcol & 63) >> 3) + g;
-              if (dual) {
-                stage_bf16x8(b1, row_in_tile, chunk16, pre);
-                stage_bf16x8(b2, row_in_tile, chunk16, v);
-              } else {
-                stage_bf16x8(b1, row_in_tile, chunk16, v);
+              for (int g = 0; g < 4; ++g) {
+                const int col = col0 + g * 8;
+                float v[8], pre[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
+                const int chunk16 = ((pcol & 63) >> 3) + g;
+                if (dual) {
+                  stage_bf16x8(staging, row_in_tile, chunk16, pre);
+                  stage_bf16x8(staging + 16384, row_in_tile, chunk16, v);
+                } else {
+                  stage_bf16x8(staging + (pcol >> 6) * 16384, row_in_tile, chunk16, v);
+                }
               }
             }
           }
@@ -398,19 +374,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           named_bar_sync(1, 32 * EPI_WARPS);
           if (issuer) {
             const int r0 = m_blk * BLOCK_M;
-            if (dual) {
-              const int c0 = n_blk * BN + ph * 128;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (c0 + h * 64 < p.N) {
-                  tma_store_2d(&tma_o1, staging + h * 16384, c0 + h * 64, r0);
-                  tma_store_2d(&tma_o2, staging + (2 + h) * 16384, c0 + h * 64, r0);
-                }
+            const int c0 = n_blk * BN + ph * pcols_max;
+            if (EPI == 2) {
+              for (int b2 = 0; b2 < 2; ++b2)
+                if (b2 * 32 < pcols && c0 + b2 * 32 < p.N) tma_reduce_add_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 32, r0);
+            } else if (dual) {
+              if (c0 < p.N) {
+                tma_store_2d(&tma_o1, staging, c0, r0);
+                tma_store_2d(&tma_o2, staging + 16384, c0, r0);
               }
             } else {
-#pragma unroll
-              for (int b = 0; b < BN / 64; ++b)
-                if (n_blk * BN + b * 64 < p.N) tma_store_2d(&tma_o1, staging + b * 16384, n_blk * BN + b * 64, r0);
+              for (int b2 = 0; b2 < 2; ++b2)
+                if (b2 * 64 < pcols && c0 + b2 * 64 < p.N) tma_store_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 64, r0);
             }
             tma_store_commit();
           }
