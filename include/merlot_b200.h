@@ -90,7 +90,8 @@ int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream);
  *  lse   : f32 [B, heads, S] log-sum-exp of the masked scaled scores (written by fwd, read by bwd / colsum).
  *  fwd   : ctx bf16 [B*S, ld_ctx] <- softmax(.) v
  *  bwd   : needs ctx, d_ctx (bf16 [B*S, ld_ctx]); writes dsum (scratch f32 [B,heads,S]), accumulates dq in dq_accum
- *          (f32 [B*S, ld_dq], MUST be zero on entry; it is re-zeroed on exit) and writes dqkv bf16 [B*S, ld_dqkv].
+ *          (f32 [B*S, ld_dq], MUST be zero on entry; it is re-zeroed on exit) and writes dqkv bf16 [B*S, ld_dqkv];
+ *          with d_bias_qkv != NULL the same pass adds colsum(dqkv) to it (bias gradient of the q/k/v tf.layers.dense).
  *  colsum: colsum[b,k] += (1/heads) * sum_q P[b,h,q,k]   (f32 [B,S]; caller zeroes it once per stack).
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct merlot_attn {
@@ -105,6 +106,7 @@ typedef struct merlot_attn {
   float* dq_accum; int ld_dq;
   void* dqkv; int ld_dqkv;
   float* colsum;
+  float* d_bias_qkv;           /* optional f32 [3H]: += column sums of dqkv (gradient of the fused q/k/v bias) */
 } merlot_attn_t;
 
 int merlot_attention_fwd(const merlot_attn_t* a, void* stream);

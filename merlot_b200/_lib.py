@@ -107,6 +107,7 @@ class AttnDesc(C.Structure):
         ("dq_accum", C.c_void_p), ("ld_dq", C.c_int),
         ("dqkv", C.c_void_p), ("ld_dqkv", C.c_int),
         ("colsum", C.c_void_p),
+        ("d_bias_qkv", C.c_void_p),
     ]
 
 

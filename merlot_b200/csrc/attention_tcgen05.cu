@@ -500,22 +500,50 @@ __global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restr
   }
 }
 
-// dq fp32 accumulator -> bf16 q-block of dqkv, and re-zero the accumulator for the next layer
-__global__ void attn_dq_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv, long long rows,
-                                      int H) {
+// dq fp32 accumulator -> bf16 q-block of dqkv (and re-zero the accumulator for the next layer), fused with the column sums
+// of the whole dqkv row block = the gradient of the fused q/k/v bias.  grid = (ceil(3H/256), row slabs), 8 warps, lane = 8 cols.
+__global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv,
+                                                               long long rows, int H, float* __restrict__ bias_grad) {
+  __shared__ float sred[8][256];
   pdl_launch_dependents();
   pdl_wait();
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int per_row = H / 8;
-  if (gid >= rows * per_row) return;
-  const long long r = gid / per_row;
-  const int c = (int)(gid % per_row) * 8;
-  float4* src = reinterpret_cast<float4*>(dq + (size_t)r * ld_dq + c);
-  float4 a = src[0], b = src[1];
-  *reinterpret_cast<uint4*>(dqkv + (size_t)r * ld_dqkv + c) =
-      make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-  src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-  src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < 3 * H) {
+    for (long long r = (long long)blockIdx.y * 8 + warp; r < rows; r += (long long)gridDim.y * 8) {
+      float v[8];
+      bf16* o = dqkv + (size_t)r * ld_dqkv + col;
+      if (col < H) {
+        float4* src = reinterpret_cast<float4*>(dq + (size_t)r * ld_dq + col);
+        const float4 a = src[0], b = src[1];
+        const uint4 pk = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        *reinterpret_cast<uint4*>(o) = pk;
+        src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t* pu = reinterpret_cast<const uint32_t*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(pu[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(o);
+        const uint32_t* pu = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(pu[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sred[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (bias_grad != nullptr && blockIdx.x * 256 + c < 3 * H) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s2 += sred[w][c];
+    atomicAdd(bias_grad + blockIdx.x * 256 + c, s2);
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -691,9 +719,10 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
   else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), BWD_SMEM, stream, tm, tdo, p));
   MB_CHECK_LAUNCH();
   {
-    const long long n = tokens * (H / 8);
-    MB_CHECK_CUDA(launch_pdl(attn_dq_finish_kernel, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, stream, a->dq_accum,
-                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H));
+    long long slabs = ceil_div_ll(tokens, 64);
+    if (slabs > 128) slabs = 128;
+    MB_CHECK_CUDA(launch_pdl(attn_dqkv_finish_kernel, dim3(ceil_div(3 * H, 256), (unsigned)slabs), dim3(256), 0, stream, a->dq_accum,
+                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv));
     MB_CHECK_LAUNCH();
   }
   return MERLOT_OK;

@@ -320,9 +320,10 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
   }
   __syncthreads();
   // block partials -> fp32 red.add straight into the gradient arena (dgamma | dbeta | bias)
-  for (int i = threadIdx.x; i < (want_bias ? 3 : 2) * H; i += blockDim.x) {
-    float* dst = i < H ? out_g + i : (i < 2 * H ? out_b + (i - H) : out_bias + (i - 2 * H));
-    atomicAdd(dst, sred[i]);
+  for (int i4 = threadIdx.x * 4; i4 < (want_bias ? 3 : 2) * H; i4 += blockDim.x * 4) {  // H % 8 == 0: a float4 never straddles
+    float* dst = i4 < H ? out_g + i4 : (i4 < 2 * H ? out_b + (i4 - H) : out_bias + (i4 - 2 * H));
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sred[i4]), "f"(sred[i4 + 1]), "f"(sred[i4 + 2]),
+                 "f"(sred[i4 + 3]) : "memory");
   }
 }
 

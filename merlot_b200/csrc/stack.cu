@@ -252,11 +252,10 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
       memset(&a, 0, sizeof(a));
       a.B = s->B; a.S = s->S; a.heads = s->heads; a.head_dim = 64; a.qkv = A.qkv; a.ld_qkv = 3 * H; a.valid = s->valid;
       a.scale = 0.125f; a.ctx = A.ctx; a.ld_ctx = H; a.lse = A.lse; a.d_ctx = dtmp; a.dsum = dsum; a.dq_accum = dq_acc;
-      a.ld_dq = H; a.dqkv = dqkv; a.ld_dqkv = 3 * H;
+      a.ld_dq = H; a.dqkv = dqkv; a.ld_dqkv = 3 * H; a.d_bias_qkv = P.g_b_qkv;  // bias gradient fused into the finish pass
       RC(merlot_attention_bwd(&a, st));
     }
     // ---- QKV projection ----
-    RC(merlot_bias_grad(dqkv, 0, 3 * H, M, 3 * H, P.g_b_qkv, 0.f, 0, 0, st));
     RC(linear_wgrad(A.x1, H, dqkv, 3 * H, P.g_w_qkv, M, st));
     RC(linear_dgrad(dqkv, 3 * H, P.w_qkv, H, dtmp, M, gemm_base(0, 0, 0), st));
     // ---- LN1: d_h_in = d_hmid + LN'(dx1); feeds the previous layer's FFN2 ----
