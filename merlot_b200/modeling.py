@@ -239,6 +239,14 @@ class MerlotModel(object):
         p_vit = float(cfg.get("vit_hidden_dropout_prob", cfg["hidden_dropout_prob"]) or 0.0) if train else 0.0
         vt = "vision_backbone/vision_transformer"
 
+        # ---- language-only encoder (:135-137) on a side stream: it only needs input_ids, and its small latency-bound grids
+        # fill the SMs the ViT kernels leave idle.  Joined before mask_inputs.
+        side = self._side_stream()
+        if self._mask_input:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._langonly_reps()
+
         # ---- ViT (utils/vision_transformer.py:173-274) ----
         img = image if image.dtype == torch.bfloat16 else image.to(torch.bfloat16)
         img = img.contiguous()
@@ -279,7 +287,7 @@ class MerlotModel(object):
         # ---- language-only encoder + masking (:135-139) ----
         ids_bl = self.input_ids.reshape(B, Lj)
         if self._mask_input:
-            self._langonly_reps()
+            torch.cuda.current_stream().wait_stream(side)
             if mask_override is not None:
                 self.lang_mask_info = {"masked_ids": mask_override["masked_ids"].to(dev).to(torch.int32).reshape(B, Lj).contiguous(),
                                        "masked_idx": mask_override["masked_idx"].to(dev).to(torch.int32).contiguous()}
@@ -301,6 +309,12 @@ class MerlotModel(object):
         self._hidden_f32 = {}
         self.encoder_pieces = [{"name": "viz", "start": 0, "end": Pz}, {"name": "lang", "start": Pz, "end": Sj}]
         self._heads = {}
+
+    def _side_stream(self):
+        st = self.store
+        if not hasattr(st, "_side"):
+            st._side = torch.cuda.Stream(device=st.device)
+        return st._side
 
     # ---------------------------------------------------------------------------------------------------------
     def _embed_words_into(self, ids_2d, norm_scope_name, tag, site, out, remap):
@@ -769,17 +783,21 @@ class MerlotModel(object):
         ops.group_rowsum(dxz, N, vcl, 0, 1, None, st.G("vision_backbone/final_pe/cls_emb"), H)
         ops.group_rowsum(dxz, N, vcl, 1, D["h2"] * D["w2"], self._grid_idxmap(D["h2"], D["w2"]),
                          st.G("vision_backbone/final_pe/pos_embs"), H)
-        # ---- language-only encoder ----
-        if self._mask_input:
-            Blo, Llo = self._ids_lo.shape
-            d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
-            ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
-            d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
-            self._lo.backward(d_ylo, d_h0lo)
-            self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
-                            Blo, Llo)
-        if on_non_vit_grads_ready is not None:
-            on_non_vit_grads_ready()
+        # ---- language-only encoder, on the side stream (independent of the ViT backward below) ----
+        side = self._side_stream()
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if self._mask_input:
+                Blo, Llo = self._ids_lo.shape
+                d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
+                ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
+                d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
+                self._lo.backward(d_ylo, d_h0lo)
+                self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
+                                Blo, Llo)
+            if on_non_vit_grads_ready is not None:
+                on_non_vit_grads_ready()  # ordered after everything queued on the side stream
         # ---- ViT ----
         d_h0v = bf.get("bwd.d_h0v", (Mv, H), torch.bfloat16)
         self._vit.backward(d_hv, d_h0v)
@@ -794,6 +812,7 @@ class MerlotModel(object):
         ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
         ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
                  out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
+        main.wait_stream(side)
     def _embed_bwd(self, tag, norm_scope_name, ids_2d, dy, remap, dropout, groups, Lseq):
         st, bf = self.store, self._bufs
         H, R = self.hidden_size, ids_2d.numel()
