@@ -15,6 +15,7 @@ from __future__ import annotations
 import copy
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -311,7 +312,10 @@ class MerlotModel(object):
         self._heads = {}
 
     def _side_stream(self):
+        """Stream for the language-only stack (set MERLOT_NO_SIDE_STREAM=1 to serialise everything on one stream)."""
         st = self.store
+        if os.environ.get("MERLOT_NO_SIDE_STREAM", "0") == "1":
+            return torch.cuda.current_stream()
         if not hasattr(st, "_side"):
             st._side = torch.cuda.Stream(device=st.device)
         return st._side
@@ -766,6 +770,20 @@ class MerlotModel(object):
         if "tmp" in self._heads:
             self._temporal_bwd(d_yj)
         p_emb = float(self.dropout_prob or 0.0)
+        # ---- language-only encoder backward on the side stream: it needs only d_lang_trg (contrastive head) and runs
+        # concurrently with the joint-encoder backward below, whose small grids leave a third of the SMs idle ----
+        side = self._side_stream()
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if self._mask_input:
+                Blo, Llo = self._ids_lo.shape
+                d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
+                ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
+                d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
+                self._lo.backward(d_ylo, d_h0lo)
+                self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
+                                Blo, Llo)
         # ---- joint encoder ----
         d_jin = bf.get("bwd.d_jin", (B * Sj, H), torch.bfloat16)
         self._joint.backward(d_yj, d_jin)
@@ -783,21 +801,10 @@ class MerlotModel(object):
         ops.group_rowsum(dxz, N, vcl, 0, 1, None, st.G("vision_backbone/final_pe/cls_emb"), H)
         ops.group_rowsum(dxz, N, vcl, 1, D["h2"] * D["w2"], self._grid_idxmap(D["h2"], D["w2"]),
                          st.G("vision_backbone/final_pe/pos_embs"), H)
-        # ---- language-only encoder, on the side stream (independent of the ViT backward below) ----
-        side = self._side_stream()
-        main = torch.cuda.current_stream()
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            if self._mask_input:
-                Blo, Llo = self._ids_lo.shape
-                d_ylo = bf.get("bwd.d_ylo", (Blo * Llo, H), torch.bfloat16, zero=True)
-                ops.scatter_add_rows(d_lang_trg, self._pool_idx_lo, d_ylo)
-                d_h0lo = bf.get("bwd.d_h0lo", (Blo * Llo, H), torch.bfloat16)
-                self._lo.backward(d_ylo, d_h0lo)
-                self._embed_bwd("emb_lo", "langonly_embeddings", self._ids_lo, d_h0lo, (0, 0, 0), (p_emb, self._seed, _SITE_EMB_LO),
-                                Blo, Llo)
-            if on_non_vit_grads_ready is not None:
-                on_non_vit_grads_ready()  # ordered after everything queued on the side stream
+        # join the language-only backward (side stream); every gradient outside the ViT is final now
+        main.wait_stream(side)
+        if on_non_vit_grads_ready is not None:
+            on_non_vit_grads_ready()
         # ---- ViT ----
         d_h0v = bf.get("bwd.d_h0v", (Mv, H), torch.bfloat16)
         self._vit.backward(d_hv, d_h0v)
@@ -812,7 +819,6 @@ class MerlotModel(object):
         ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
         ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
                  out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
-        main.wait_stream(side)
     def _embed_bwd(self, tag, norm_scope_name, ids_2d, dy, remap, dropout, groups, Lseq):
         st, bf = self.store, self._bufs
         H, R = self.hidden_size, ids_2d.numel()

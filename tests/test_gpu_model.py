@@ -171,7 +171,10 @@ def test_full_size_properties():
     spec.model.backward()
     g1 = store.g.clone()
     spec.model.backward()
-    assert rel(store.g, 2 * g1) < 2e-3  # atomics reorder fp32 sums; linear accumulation otherwise
+    # Accumulation is linear; the backward itself is not bit-reproducible: dQ is reduced with fp32 atomics, its bf16
+    # rounding flips on ~1e-5 of the elements and 12 pre-LN layers amplify that to ~3e-3 run-to-run on the earliest
+    # layers' gradients (tools/determinism_check.py, tools/op_determinism.py: every other op is bitwise repeatable).
+    assert rel(store.g, 2 * g1) < 1e-2
     assert torch.isfinite(g1).all() and float(g1.abs().max()) > 0
     store.g.zero_()
     l0 = spec.loss
