@@ -1,0 +1,150 @@
+// Shared pieces of the K1 GEMM kernels (1-CTA and CTA-pair variants): tile constants, the device-side problem descriptor and the
+// fused epilogue math / store helpers.
+#pragma once
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SMEM_LIMIT = 232448 - 1024 - 256;  // 227 KB minus alignment slack and barriers
+constexpr int STAGING_BYTES = 32768;             // 2 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
+
+struct GemmDev {
+  int M, N, K;
+  int splits, kb_per_split, num_kb;
+  int m_blocks, n_blocks;
+  void* out; int ld_out;
+  void* out2; int ld_out2;
+  const float* bias;
+  const bf16* resid; int ld_resid;
+  const bf16* aux; int ld_aux;
+  float alpha;
+  uint32_t flags;
+  uint32_t drop_thresh16; float drop_scale; uint64_t seed; uint32_t site;
+};
+
+template <int BN, int EPI>
+struct GemmCfg {
+  static constexpr bool TS = EPI != 0;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - (TS ? STAGING_BYTES : 0)) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator stages, power-of-two allocation
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + (TS ? STAGING_BYTES : 0) + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Fused epilogue math for 8 consecutive columns [col, col+8) of one row, in registers.
+//   v = alpha*acc (+bias); GELU: pre <- v, v <- gelu(v); MUL_DGELU: v *= gelu'(aux); DROPOUT; (+resid)
+// `in_range` = row < M (global loads are skipped for padding rows; their results are clipped on store).
+__device__ __forceinline__ void epi_math8(const GemmDev& p, int row, int col, bool in_range, float (&v)[8], float (&pre)[8]) {
+  const bool full = (col + 8 <= p.N);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
+  if (p.bias != nullptr) {
+    if (full) {
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
+    }
+  }
+  if (p.flags & MERLOT_GEMM_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pre[i] = v[i]; v[i] = gelu_erf_fast(v[i]); }
+  }
+  if ((p.flags & MERLOT_GEMM_MUL_DGELU) && in_range) {
+    const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
+    if (full) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(a));
+      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      v[0] *= gelu_erf_grad_fast(f0.x); v[1] *= gelu_erf_grad_fast(f0.y); v[2] *= gelu_erf_grad_fast(f1.x);
+      v[3] *= gelu_erf_grad_fast(f1.y); v[4] *= gelu_erf_grad_fast(f2.x); v[5] *= gelu_erf_grad_fast(f2.y);
+      v[6] *= gelu_erf_grad_fast(f3.x); v[7] *= gelu_erf_grad_fast(f3.y);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] *= gelu_erf_grad_fast(__bfloat162float(a[i]));
+    }
+  }
+  if (p.flags & MERLOT_GEMM_DROPOUT) {
+    uint64_t lin = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;  // col % 8 == 0, N % 8 == 0 enforced on host
+    uint32_t keep = dropout_keep8(p.seed, p.site, lin >> 3, p.drop_thresh16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.0f;
+  }
+  if (p.resid != nullptr && in_range) {
+    const bf16* r = p.resid + (size_t)row * p.ld_resid + col;
+    if (full) {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(r));
+      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y; v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) v[i] += __bfloat162float(r[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_bf16x8(bf16* o, int col, int N, const float (&v)[8]) {
+  if (col + 8 <= N) {
+    *reinterpret_cast<uint4*>(o) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (col + i < N) o[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// direct (register -> global) store path: fp32 outputs, atomics, and bf16 fallbacks
+__device__ __forceinline__ void epi_store_direct(const GemmDev& p, int row, int col, const float (&v)[8], const float (&pre)[8]) {
+  const bool full = (col + 8 <= p.N);
+  const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
+  if (p.flags & MERLOT_GEMM_OUT_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ld_out + col;
+    if (p.flags & MERLOT_GEMM_ATOMIC) {
+      if (full) {
+        red_add_v4(o, v[0], v[1], v[2], v[3]);
+        red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < p.N) atomicAdd(o + i, v[i]);
+      }
+    } else if (full && ((p.ld_out & 3) == 0)) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col + i < p.N) o[i] = v[i];
+    }
+  } else if (dual) {
+    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, pre);
+    store_bf16x8(reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ld_out2 + col, col, p.N, v);
+  } else {
+    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, v);
+  }
+}
+
+__device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int chunk16, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)chunk16)) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+
+}  // namespace mb

@@ -6,152 +6,13 @@
 // the epilogue of tile i overlaps the main loop of tile i+1), and a static persistent tile schedule.
 //
 // Replaces the reference's tf.layers.dense / tf.matmul call sites listed in include/merlot_b200.h (K1).
-#include "host_common.h"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
+
+#include <stdlib.h>
 
 #include <vector>
 
 namespace mb {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle atom
-constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each owning half of the tile's columns
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_LIMIT = 232448 - 1024 - 256;  // 227 KB minus alignment slack and barriers
-constexpr int STAGING_BYTES = 32768;             // 2 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
-
-struct GemmDev {
-  int M, N, K;
-  int splits, kb_per_split, num_kb;
-  int m_blocks, n_blocks;
-  void* out; int ld_out;
-  void* out2; int ld_out2;
-  const float* bias;
-  const bf16* resid; int ld_resid;
-  const bf16* aux; int ld_aux;
-  float alpha;
-  uint32_t flags;
-  uint32_t drop_thresh16; float drop_scale; uint64_t seed; uint32_t site;
-};
-
-template <int BN, int EPI>
-struct GemmCfg {
-  static constexpr bool TS = EPI != 0;
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_LIMIT - (TS ? STAGING_BYTES : 0)) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;  // two accumulator stages, power-of-two allocation
-  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + (TS ? STAGING_BYTES : 0) + 1024 + 256;
-};
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// Fused epilogue math for 8 consecutive columns [col, col+8) of one row, in registers.
-//   v = alpha*acc (+bias); GELU: pre <- v, v <- gelu(v); MUL_DGELU: v *= gelu'(aux); DROPOUT; (+resid)
-// `in_range` = row < M (global loads are skipped for padding rows; their results are clipped on store).
-__device__ __forceinline__ void epi_math8(const GemmDev& p, int row, int col, bool in_range, float (&v)[8], float (&pre)[8]) {
-  const bool full = (col + 8 <= p.N);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] *= p.alpha;
-  if (p.bias != nullptr) {
-    if (full) {
-      float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) v[i] += __ldg(p.bias + col + i);
-    }
-  }
-  if (p.flags & MERLOT_GEMM_GELU) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { pre[i] = v[i]; v[i] = gelu_erf_fast(v[i]); }
-  }
-  if ((p.flags & MERLOT_GEMM_MUL_DGELU) && in_range) {
-    const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
-    if (full) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(a));
-      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      v[0] *= gelu_erf_grad_fast(f0.x); v[1] *= gelu_erf_grad_fast(f0.y); v[2] *= gelu_erf_grad_fast(f1.x);
-      v[3] *= gelu_erf_grad_fast(f1.y); v[4] *= gelu_erf_grad_fast(f2.x); v[5] *= gelu_erf_grad_fast(f2.y);
-      v[6] *= gelu_erf_grad_fast(f3.x); v[7] *= gelu_erf_grad_fast(f3.y);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) v[i] *= gelu_erf_grad_fast(__bfloat162float(a[i]));
-    }
-  }
-  if (p.flags & MERLOT_GEMM_DROPOUT) {
-    uint64_t lin = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;  // col % 8 == 0, N % 8 == 0 enforced on host
-    uint32_t keep = dropout_keep8(p.seed, p.site, lin >> 3, p.drop_thresh16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.0f;
-  }
-  if (p.resid != nullptr && in_range) {
-    const bf16* r = p.resid + (size_t)row * p.ld_resid + col;
-    if (full) {
-      uint4 u = __ldg(reinterpret_cast<const uint4*>(r));
-      float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y; v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) v[i] += __bfloat162float(r[i]);
-    }
-  }
-}
-
-__device__ __forceinline__ void store_bf16x8(bf16* o, int col, int N, const float (&v)[8]) {
-  if (col + 8 <= N) {
-    *reinterpret_cast<uint4*>(o) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (col + i < N) o[i] = __float2bfloat16_rn(v[i]);
-  }
-}
-
-// direct (register -> global) store path: fp32 outputs, atomics, and bf16 fallbacks
-__device__ __forceinline__ void epi_store_direct(const GemmDev& p, int row, int col, const float (&v)[8], const float (&pre)[8]) {
-  const bool full = (col + 8 <= p.N);
-  const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
-  if (p.flags & MERLOT_GEMM_OUT_F32) {
-    float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ld_out + col;
-    if (p.flags & MERLOT_GEMM_ATOMIC) {
-      if (full) {
-        red_add_v4(o, v[0], v[1], v[2], v[3]);
-        red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < p.N) atomicAdd(o + i, v[i]);
-      }
-    } else if (full && ((p.ld_out & 3) == 0)) {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (col + i < p.N) o[i] = v[i];
-    }
-  } else if (dual) {
-    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, pre);
-    store_bf16x8(reinterpret_cast<bf16*>(p.out2) + (size_t)row * p.ld_out2 + col, col, p.N, v);
-  } else {
-    store_bf16x8(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ld_out + col, col, p.N, v);
-  }
-}
-
-__device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int chunk16, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)chunk16)) =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
 
 // TS = true: bf16 outputs leave through 128B-swizzled smem staging boxes and TMA stores (fully coalesced, edge clipping
 // by the tensor map).  TS = false: direct register->global stores (fp32 outputs / atomics).
@@ -437,6 +298,11 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
 
 }  // namespace mb
 
+namespace mb {
+int launch_gemm_pair(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1,
+                     const CUtensorMap& to2, const GemmDev& p, int grid, cudaStream_t stream);
+}
+
 using namespace mb;
 
 extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
@@ -488,6 +354,11 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   p.num_kb = ceil_div(g->K, BLOCK_K);
   // ---- tile width: minimise wave-quantisation loss; BN=256 halves per-FLOP smem traffic so it wins ties ----
   int bn = g->block_n;
+  // CTA-pair kernel (cta_group::2, 256 x 256 tile): block_n = -256 forces it; MERLOT_GEMM_PAIR=1 lets the heuristic pick it
+  // (measured: 8192^3 1464 vs 1305 TF/s, split-K wgrad 1281 vs 1208; a wash at K = 768 where tile quantisation dominates)
+  static const int pair_auto = [] { const char* e = getenv("MERLOT_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  bool pair = false;
+  if (bn == -256) { pair = true; bn = 256; }
   if (bn == 0 && (g->flags & MERLOT_GEMM_ATOMIC)) bn = 256;  // wgrad: split-K fills the machine, wide tiles halve smem traffic
   if (bn == 0) {
     const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
@@ -504,13 +375,17 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   MB_REQUIRE(bn == 128 || bn == 192 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128, 192 or 256 (got %d)", bn);
   MB_REQUIRE(!(bn == 192 && (g->flags & MERLOT_GEMM_GELU) && g->out2), MERLOT_EINVAL, "gemm: block_n 192 cannot be used with a dual (pre+act) output");
   p.n_blocks = ceil_div(g->N, bn);
+  if (!pair && pair_auto == 2 && bn == 256 && g->M > 256) pair = true;  // 2 = everywhere (experiments)
+  if (!pair && pair_auto == 1 && bn == 256 && g->M > 256 && ((g->flags & MERLOT_GEMM_ATOMIC) || g->K >= 4096)) pair = true;
+  const int units = pair ? sms / 2 : sms;                                   // schedulable CTAs or CTA pairs
+  const int m_tiles = pair ? ceil_div(g->M, 256) : p.m_blocks;
   // ---- split-K (wgrad): fill the machine when the MN tile count is small ----
   int splits = g->splits;
-  const int mn_tiles = p.m_blocks * p.n_blocks;
+  const int mn_tiles = m_tiles * p.n_blocks;
   if (splits <= 0) {
     splits = 1;
-    if ((g->flags & MERLOT_GEMM_ATOMIC) && mn_tiles < sms) {
-      splits = sms / mn_tiles;
+    if ((g->flags & MERLOT_GEMM_ATOMIC) && mn_tiles < units) {
+      splits = units / mn_tiles;
       int max_by_k = p.num_kb / 4 > 0 ? p.num_kb / 4 : 1;  // keep >= 4 k-blocks per split
       if (splits > max_by_k) splits = max_by_k;
       if (splits < 1) splits = 1;
@@ -531,11 +406,11 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   if (g->b_mn_major)
     rc = make_tmap_bf16_2d(&tb, g->b, (uint64_t)g->N, (uint64_t)g->K, (uint64_t)g->ldb, 64, BLOCK_K);
   else
-    rc = make_tmap_bf16_2d(&tb, g->b, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BLOCK_K, (uint32_t)bn);
+    rc = make_tmap_bf16_2d(&tb, g->b, (uint64_t)g->K, (uint64_t)g->N, (uint64_t)g->ldb, BLOCK_K, (uint32_t)(pair ? bn / 2 : bn));
   if (rc) return rc;
 
   const long long tiles = (long long)mn_tiles * p.splits;
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  const int grid = pair ? 2 * (int)(tiles < units ? tiles : units) : (int)(tiles < sms ? tiles : sms);
 
   // epilogue route: 1 = bf16 tiles through swizzled smem staging + TMA store; 2 = fp32 split-K accumulation through TMA
   // reduce-add (plain alpha*acc only); 0 = direct register->global stores (other fp32 outputs)
@@ -557,6 +432,7 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
     rc = make_tmap_f32_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 32, BLOCK_M);
     if (rc) return rc;
   }
+  if (pair) return launch_gemm_pair(g->a_mn_major != 0, g->b_mn_major != 0, epi, ta, tb, to1, to2, p, grid, stream);
 #define MB_GEMM_DISPATCH2(BN_, EPI_)                                                                                  \
   if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true, EPI_>(ta, tb, to1, to2, p, grid, stream);   \
   if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true, EPI_>(ta, tb, to1, to2, p, grid, stream); \

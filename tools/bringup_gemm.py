@@ -117,11 +117,72 @@ def run_perf():
     return True
 
 
+def run_pair():
+    """CTA-pair (cta_group::2) kernel: block_n = -256."""
+    dev = "cuda"
+    ok = True
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for (a_mn, b_mn) in [(False, False), (False, True), (True, True), (True, False)]:
+        for (M, N, K) in [(256, 256, 64), (256, 256, 256), (512, 512, 768), (520, 768, 136), (8512, 2304, 768), (1000, 264, 3072)]:
+            if (M % 8 and a_mn) or (N % 8 and b_mn):
+                continue
+            a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.5).bfloat16().to(dev)
+            b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.5).bfloat16().to(dev)
+            for f32 in (True, False):
+                out = ops.gemm(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32 if f32 else torch.bfloat16, block_n=-256)
+                torch.cuda.synchronize()
+                ok &= check(f"pair a_mn={a_mn} b_mn={b_mn} M={M} N={N} K={K} f32={f32}", out, ref_mm(a, b, a_mn, b_mn), 1e-3 if f32 else 6e-3)
+    # epilogues through the pair kernel
+    M, N, K = 520, 768, 768
+    a = (torch.randn(M, K, generator=g) * 0.3).bfloat16().to(dev)
+    w = (torch.randn(K, N, generator=g) * 0.05).bfloat16().to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    resid = torch.randn(M, N, generator=g).bfloat16().to(dev)
+    base = a.float() @ w.float() + bias
+    ok &= check("pair bias+resid", ops.gemm(a, w, b_mn_major=True, bias=bias, resid=resid, block_n=-256), base + resid.float(), 6e-3)
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    act = ops.gemm(a, w, b_mn_major=True, bias=bias, gelu=True, out_pre=pre, block_n=-256)
+    ok &= check("pair gelu pre", pre, base, 6e-3)
+    ok &= check("pair gelu act", act, torch.nn.functional.gelu(base), 6e-3)
+    dy = (torch.randn(M, N, generator=g) * 0.1).bfloat16().to(dev)
+    dw = torch.zeros(K, N, dtype=torch.float32, device=dev)
+    for _ in range(2):
+        ops.gemm(a, dy, a_mn_major=True, b_mn_major=True, out=dw, atomic=True, M=K, N=N, K=M, block_n=-256)
+    ok &= check("pair wgrad reduce-add x2", dw, 2 * (a.float().t() @ dy.float()), 1e-3)
+    return ok
+
+
+def run_pair_perf():
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(2)
+    for (M, N, K, a_mn, b_mn, f32) in [(8512, 2304, 768, 0, 1, 0), (8512, 768, 768, 0, 1, 0), (8512, 3072, 768, 0, 1, 0),
+                                       (8512, 768, 3072, 0, 0, 0), (768, 3072, 8512, 1, 1, 1), (3168, 2304, 768, 0, 1, 0),
+                                       (8192, 8192, 8192, 0, 0, 0)]:
+        a = (torch.randn((K, M) if a_mn else (M, K), generator=g) * 0.1).bfloat16().to(dev)
+        b = (torch.randn((K, N) if b_mn else (N, K), generator=g) * 0.1).bfloat16().to(dev)
+        for bn in (0, -256):
+            out = torch.zeros(M, N, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
+            kw = dict(a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), out=out, atomic=bool(f32), block_n=bn)
+            for _ in range(3):
+                ops.gemm(a, b, **kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ops.gemm(a, b, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"perf M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} {'PAIR' if bn else 'auto'}: {ms * 1e3:.1f} us  "
+                  f"{2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    return True
+
+
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "kk"
     t0 = time.time()
     ok = {"kk": lambda: run_major(False, False), "kmn": lambda: run_major(False, True),
           "mnmn": lambda: run_major(True, True), "mnk": lambda: run_major(True, False),
-          "epi": run_epi, "perf": run_perf}[mode]()
+          "epi": run_epi, "perf": run_perf, "pair": run_pair, "pairperf": run_pair_perf}[mode]()
     print(f"[{mode}] {'PASS' if ok else 'FAIL'} in {time.time() - t0:.1f}s", flush=True)
     sys.exit(0 if ok else 1)
