@@ -107,11 +107,18 @@ typedef struct merlot_attn {
   void* dqkv; int ld_dqkv;
   float* colsum;
   float* d_bias_qkv;           /* optional f32 [3H]: += column sums of dqkv (gradient of the fused q/k/v bias) */
+  float* colsum2;              /* colsum only: queries >= colsum_split accumulate here instead of `colsum` (optional) */
+  int colsum_split;
+  int colsum_valid_q;          /* colsum only: 1 = padding queries contribute nothing (attention_log, modeling.py:192-193) */
 } merlot_attn_t;
 
 int merlot_attention_fwd(const merlot_attn_t* a, void* stream);
 int merlot_attention_bwd(const merlot_attn_t* a, void* stream);
 int merlot_attention_colsum(const merlot_attn_t* a, void* stream);
+/* attention_log (model/modeling.py:186-203): out4 = {lang2lang, lang2viz, viz2lang, viz2viz} normalised block sums of the
+ * layer/head/batch-mean attention map, from the two split column sums (queries in the viz piece / in the lang piece). */
+int merlot_attention_log_blocks(const float* c_viz, const float* c_lang, const void* valid_u8, int B, int S, int P, float* out4,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K5: LayerNorm (utils/model_utils.py:113-130): fp32 statistics over the last dim, biased variance, eps inside rsqrt,
@@ -211,6 +218,7 @@ typedef struct merlot_stack {
   int save_for_backward;                       /* 0: forward only (arena holds one layer) */
   float hidden_dropout_p; float attention_dropout_p; uint64_t dropout_seed; uint32_t dropout_site_base;
   float* attn_colsum;                          /* optional f32 [B,S]: += sum over layers,queries of head-mean probs */
+  float* attn_colsum2; int attn_colsum_split; int attn_colsum_valid_q;  /* optional split by query piece (attention_log) */
   /* backward */
   const void* dy;                              /* bf16 [B*S, H] gradient wrt y */
   void* dh_in;                                 /* bf16 [B*S, H] gradient wrt h_in (optional) */
@@ -268,6 +276,9 @@ typedef struct merlot_adamw {
   int zero_grad;
 } merlot_adamw_t;
 int merlot_adamw_step(const merlot_adamw_t* d, void* stream);
+/* tf.clip_by_global_norm over the flat gradient arena (utils/optimization.py:233-237); scratch_f64 = one device double;
+ * norm_out (optional device float) receives the pre-clip global norm (the reference's gradnorms/_overall metric). */
+int merlot_clip_by_global_norm(float* g, long long n, float clip_norm, double* scratch_f64, float* norm_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Loss-head glue (model/modeling.py:491-668): integer index/label construction and weighted reductions, on device.

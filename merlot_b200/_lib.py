@@ -108,6 +108,7 @@ class AttnDesc(C.Structure):
         ("dqkv", C.c_void_p), ("ld_dqkv", C.c_int),
         ("colsum", C.c_void_p),
         ("d_bias_qkv", C.c_void_p),
+        ("colsum2", C.c_void_p), ("colsum_split", C.c_int), ("colsum_valid_q", C.c_int),
     ]
 
 
@@ -159,6 +160,7 @@ class StackDesc(C.Structure):
         ("hidden_dropout_p", C.c_float), ("attention_dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
         ("dropout_site_base", C.c_uint32),
         ("attn_colsum", C.c_void_p),
+        ("attn_colsum2", C.c_void_p), ("attn_colsum_split", C.c_int), ("attn_colsum_valid_q", C.c_int),
         ("dy", C.c_void_p),
         ("dh_in", C.c_void_p),
         ("scratch", C.c_void_p),

@@ -76,9 +76,64 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamDev a) {
   }
 }
 
+// tf.clip_by_global_norm (utils/optimization.py:233-237): norm = sqrt(sum g^2) over the whole arena, then
+// g *= clip_norm / max(norm, clip_norm).  Two launches; the norm stays on the device (also reported as gradnorms/_overall).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ acc) {
+  __shared__ double sred[8];
+  double s = 0.0;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    } else {
+      for (long long j = i; j < n; ++j) s += (double)g[j] * g[j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sred[w];
+    atomicAdd(acc, t);
+  }
+}
+__global__ void __launch_bounds__(256) clip_scale_kernel(float* __restrict__ g, long long n, const double* __restrict__ acc, float clip_norm,
+                                                         float* __restrict__ norm_out) {
+  const float norm = (float)sqrt(*acc);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) *norm_out = norm;
+  const float scale = clip_norm / fmaxf(norm, clip_norm);
+  if (scale == 1.0f) return;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      float4 v = *reinterpret_cast<float4*>(g + i);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      *reinterpret_cast<float4*>(g + i) = v;
+    } else {
+      for (long long j = i; j < n; ++j) g[j] *= scale;
+    }
+  }
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int merlot_clip_by_global_norm(float* g, long long n, float clip_norm, double* scratch_f64, float* norm_out, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(g && scratch_f64, MERLOT_EINVAL, "clip_by_global_norm: null pointer");
+  MB_REQUIRE(clip_norm > 0.f && ((uintptr_t)g % 16) == 0, MERLOT_EINVAL, "clip_by_global_norm: clip_norm must be > 0 and g 16-byte aligned");
+  if (n <= 0) return MERLOT_OK;
+  MB_CHECK_CUDA(cudaMemsetAsync(scratch_f64, 0, sizeof(double), st));
+  const int grid = 148 * 8;
+  sumsq_kernel<<<grid, 256, 0, st>>>(g, n, scratch_f64);
+  MB_CHECK_LAUNCH();
+  clip_scale_kernel<<<grid, 256, 0, st>>>(g, n, scratch_f64, clip_norm, norm_out);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
 
 extern "C" int merlot_adamw_step(const merlot_adamw_t* d, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);

@@ -33,6 +33,9 @@ struct AttnDev {
   bf16* dqkv; int ld_dqkv;       // bf16 [B*S, 3H]; this kernel writes the K and V column blocks
   // K4
   float* colsum;                 // [B, S] += sum_q mean_h P[b,h,q,k]
+  float* colsum2;                // optional: queries >= colsum_split accumulate here instead
+  int colsum_split;              // 0 = no split
+  int colsum_valid_q;            // 1 = only valid (non-padding) queries contribute (attention_log, modeling.py:192-193)
 };
 
 // score in the log2 domain: sc2 = scale * log2(e)
@@ -587,7 +590,8 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   const bool vk = k_in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
   constexpr uint32_t idesc = make_idesc_bf16(AT_N, AT_M, 0, 0);
   const float sc2 = p.scale * LOG2E;
-  float acc = 0.f;
+  float acc = 0.f, acc2 = 0.f;
+  const int split = p.colsum2 ? p.colsum_split : 0x7fffffff;
   for (int i = 0; i < n_q; ++i) {
     const uint32_t ph = i & 1;
     const int q0 = i * AT_M;
@@ -622,14 +626,18 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
         if (q < S && k_in) {
           const bool vq = p.valid ? p.valid[tok0 + q] != 0 : true;
           float x = masked_score(__uint_as_float(r[e]), sc2, vq, vk, true);
-          acc += exp2f(x - s_lse[ql]);
+          const float pr = (p.colsum_valid_q && !vq) ? 0.f : exp2f(x - s_lse[ql]);
+          if (q < split) acc += pr; else acc2 += pr;
         }
       }
     }
     tc_fence_before();
     __syncthreads();
   }
-  if (k_in) atomicAdd(p.colsum + (size_t)b * S + kk, acc / (float)p.heads);
+  if (k_in) {
+    atomicAdd(p.colsum + (size_t)b * S + kk, acc / (float)p.heads);
+    if (p.colsum2) atomicAdd(p.colsum2 + (size_t)b * S + kk, acc2 / (float)p.heads);
+  }
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
@@ -655,6 +663,9 @@ static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
   p->dq_accum = a->dq_accum; p->ld_dq = a->ld_dq;
   p->dqkv = reinterpret_cast<bf16*>(a->dqkv); p->ld_dqkv = a->ld_dqkv;
   p->colsum = a->colsum;
+  p->colsum2 = a->colsum2;
+  p->colsum_split = a->colsum_split;
+  p->colsum_valid_q = a->colsum_valid_q;
 }
 
 }  // namespace mb
@@ -725,6 +736,45 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
                              a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv));
     MB_CHECK_LAUNCH();
   }
+  return MERLOT_OK;
+}
+
+// attention_log (model/modeling.py:186-203): 4 normalised block sums from the split column sums.
+//   c_viz[b,k] / c_lang[b,k] = sum over (layers, valid queries in the viz / lang piece) of head-mean probabilities
+//   out = {lang2lang, lang2viz, viz2lang, viz2viz}  (names are `from`2`to`: keys are `from`, queries are `to`), sum = 1
+__global__ void attn_log_blocks_kernel(const float* __restrict__ c_viz, const float* __restrict__ c_lang, const uint8_t* __restrict__ valid,
+                                       int B, int S, int P, float* __restrict__ out) {
+  __shared__ float red[4][256];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};  // [to_viz_from_viz, to_viz_from_lang, to_lang_from_viz, to_lang_from_lang]
+  for (int i = threadIdx.x; i < B * S; i += 256) {
+    const int k = i % S;
+    const float vk = valid[i] ? 1.f : 0.f;
+    const int from_lang = k >= P;
+    a[0 + from_lang] += c_viz[i] * vk;
+    a[2 + from_lang] += c_lang[i] * vk;
+  }
+  for (int j = 0; j < 4; ++j) red[j][threadIdx.x] = a[j];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int j = 0; j < 4; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float tot = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+    out[0] = red[3][0] / tot;  // lang2lang : keys lang, queries lang
+    out[1] = red[1][0] / tot;  // lang2viz  : keys lang, queries viz
+    out[2] = red[2][0] / tot;  // viz2lang  : keys viz,  queries lang
+    out[3] = red[0][0] / tot;  // viz2viz
+  }
+}
+
+extern "C" int merlot_attention_log_blocks(const float* c_viz, const float* c_lang, const void* valid, int B, int S, int P, float* out4,
+                                           void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(c_viz && c_lang && valid && out4, MERLOT_EINVAL, "attention_log_blocks: null pointer");
+  attn_log_blocks_kernel<<<1, 256, 0, stream>>>(c_viz, c_lang, reinterpret_cast<const uint8_t*>(valid), B, S, P, out4);
+  MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }
 

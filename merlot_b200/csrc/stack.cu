@@ -148,6 +148,7 @@ extern "C" int merlot_stack_forward(const merlot_stack_t* s, void* stream_) {
       RC(merlot_attention_fwd(&a, st));
       if (s->attn_colsum) {
         a.colsum = s->attn_colsum;
+        a.colsum2 = s->attn_colsum2; a.colsum_split = s->attn_colsum_split; a.colsum_valid_q = s->attn_colsum_valid_q;
         RC(merlot_attention_colsum(&a, st));
       }
     }

@@ -85,7 +85,8 @@ def _layer_params(store: ParamStore, scope: str, layers: int):
 class _Stack:
     """One transformer stack invocation (utils/transformer.py:171-247) through merlot_stack_forward/backward."""
 
-    def __init__(self, store, bufs, tag, scope, layers, B, S, valid, h_in, cfg, dropout_p, seed, site, save, colsum=None):
+    def __init__(self, store, bufs, tag, scope, layers, B, S, valid, h_in, cfg, dropout_p, seed, site, save, colsum=None,
+                 colsum2=None, colsum_split=0, colsum_valid_q=0):
         H, I, heads = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_attention_heads"]
         if H % heads != 0 or H // heads != 64:
             raise ValueError("passed in a tensor of shape {} when size_per_head={} and num_attention_heads={}".format(
@@ -108,6 +109,8 @@ class _Stack:
         self.arena = bufs.get(f"{tag}.act", (L.lib().merlot_stack_activation_bytes(C.byref(d)),), torch.uint8)
         d.act_arena = self.arena.data_ptr()
         d.attn_colsum = colsum.data_ptr() if colsum is not None else None
+        d.attn_colsum2 = colsum2.data_ptr() if colsum2 is not None else None
+        d.attn_colsum_split, d.attn_colsum_valid_q = int(colsum_split), int(colsum_valid_q)
         self.d, self.bufs, self.tag, self.keep = d, bufs, tag, (valid, h_in, colsum)
 
     def forward(self):
@@ -303,9 +306,21 @@ class MerlotModel(object):
         self._embed_words_into(self._ids_j, "position_embeddings", "emb_j", _SITE_EMB_J, joint_in, remap=(Lj, Sj, Pz))
         valid_j = bf.get("joint.valid", (B * Sj,), torch.uint8)
         ops.joint_valid(self._ids_j, valid_j, B, Pz, Lj)
+        c_viz = c_lang = None
+        if self._log_attention_probs:  # split column sums of the joint attention maps for attention_log (:186-203)
+            c_viz = bf.get("joint.c_viz", (B * Sj,), torch.float32, zero=True)
+            c_lang = bf.get("joint.c_lang", (B * Sj,), torch.float32, zero=True)
         self._joint = _Stack(st, bf, "joint", "encoder", cfg["num_hidden_layers"], B, Sj, valid_j, joint_in, cfg,
-                             p_hid if train else 0.0, self._seed, _SITE_JOINT, self._save)
+                             p_hid if train else 0.0, self._seed, _SITE_JOINT, self._save, colsum=c_viz, colsum2=c_lang,
+                             colsum_split=Pz, colsum_valid_q=1)
         self._y_j = self._joint.forward()
+        self._attn_log = None
+        if self._log_attention_probs:
+            out4 = bf.get("joint.attn_log", (4,), torch.float32)
+            L.check(L.lib().merlot_attention_log_blocks(C.c_void_p(c_viz.data_ptr()), C.c_void_p(c_lang.data_ptr()),
+                                                        C.c_void_p(valid_j.data_ptr()), B, Sj, Pz, C.c_void_p(out4.data_ptr()),
+                                                        ops._stream()))
+            self._attn_log = out4
         self.encoder_info = {"hidden_state": self._y_j.view(B, Sj, H)}
         self._hidden_f32 = {}
         self.encoder_pieces = [{"name": "viz", "start": 0, "end": Pz}, {"name": "lang", "start": Pz, "end": Sj}]
@@ -444,8 +459,11 @@ class MerlotModel(object):
 
     @property
     def attention_log(self):
-        raise NotImplementedError("attention_log metrics (model/modeling.py:186-203) are not provided yet; they are "
-                                  "logging-only and carry no gradient")
+        """{'encoder/lang2lang', 'encoder/lang2viz', 'encoder/viz2lang', 'encoder/viz2viz'} (:186-203); logging only."""
+        if self._attn_log is None:
+            raise ValueError("attention_log needs log_attention_probs=True at construction (model/modeling.py:186)")
+        names = ("lang2lang", "lang2viz", "viz2lang", "viz2viz")
+        return {f"encoder/{n}": self._attn_log[i] for i, n in enumerate(names)}
 
     # ---------------------------------------------------------------------------------------------------------
     # heads

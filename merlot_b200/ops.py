@@ -365,3 +365,8 @@ def adamw_step(p, g, m, v, p_bf16, n, beta1, omb1, beta2, omb2, eps, lr_t, wd, g
     d.beta1, d.one_minus_beta1, d.beta2, d.one_minus_beta2 = beta1, omb1, beta2, omb2
     d.epsilon, d.lr_t, d.weight_decay, d.grad_scale, d.zero_grad = eps, lr_t, wd, grad_scale, int(zero_grad)
     L.check(L.lib().merlot_adamw_step(C.byref(d), _stream()))
+
+
+def clip_by_global_norm(g, clip_norm, scratch_f64, norm_out):
+    L.check(L.lib().merlot_clip_by_global_norm(C.c_void_p(g.data_ptr()), C.c_longlong(g.numel()), C.c_float(clip_norm),
+                                               C.c_void_p(scratch_f64.data_ptr()), C.c_void_p(_ptr(norm_out)), _stream()))

@@ -37,9 +37,7 @@ class AdamOptimizer:
             raise ValueError("Adafactor not supported rn")  # optimization.py:178-179
         if not use_bfloat16_adam:
             raise NotImplementedError("use_bfloat16_adam: False (fp32 Adam moments) is not provided; every shipped config sets True")
-        if clip_norm and clip_norm > 0.0:
-            raise NotImplementedError("clip_norm > 0 (tf.clip_by_global_norm, optimization.py:233-237) is not provided yet; "
-                                      "every shipped config sets clip_norm: 0.0")
+        self.clip_norm = float(clip_norm or 0.0)
         self.store = store
         self.learning_rate = learning_rate
         self.num_train_steps, self.num_warmup_steps = num_train_steps, num_warmup_steps
@@ -96,6 +94,18 @@ class AdamOptimizer:
                 st.g[a:b].zero_()
         if advance:
             st.global_step += 1  # :251-253
+
+    def clip_gradients(self):
+        """tf.clip_by_global_norm on the LOCAL gradients -- the reference clips before CrossShardOptimizer averages
+        (utils/optimization.py:233-245).  Returns the pre-clip global norm (0-d CUDA tensor) or None when clip_norm == 0."""
+        if self.clip_norm <= 0.0:
+            return None
+        st = self.store
+        if not hasattr(st, "_clip_scratch"):
+            st._clip_scratch = torch.zeros(1, dtype=torch.float64, device=st.device)
+            st._clip_norm = torch.zeros(1, dtype=torch.float32, device=st.device)
+        ops.clip_by_global_norm(st.g, self.clip_norm, st._clip_scratch, st._clip_norm)
+        return st._clip_norm[0]
 
     def current_lr(self):
         return float(np.float32(self.learning_rate) * learning_rate_scale(self.store.global_step, self.num_train_steps,

@@ -140,7 +140,13 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
         def train_op():
             world = dist.world if dist is not None else 1
             pending = []
-            if world > 1:
+            if optimizer.clip_norm > 0.0:  # local clip needs the complete local gradient first: no bucket overlap
+                model.backward()
+                losses["gradnorms/_overall"] = optimizer.clip_gradients()
+                if world > 1:
+                    dist.all_reduce_grads(store.g)
+                optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True)
+            elif world > 1:
                 # bucket 1 (everything outside the ViT) is all-reduced while the ViT backward runs; bucket 2 (ViT) is
                 # all-reduced while AdamW updates bucket 1
                 model.backward(on_non_vit_grads_ready=lambda: pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges)))

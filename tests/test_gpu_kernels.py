@@ -237,3 +237,19 @@ def test_adamw_vs_oracle(ops):
         assert torch.equal(d["v"].cpu(), opt.v[k]), "packed second moment must be bit-exact"
         assert (d["p"].cpu() - p_ref[k]).abs().max().item() < 1e-6
         assert torch.equal(d["pb"].cpu(), d["p"].cpu().bfloat16())
+
+
+def test_clip_by_global_norm(ops):
+    """tf.clip_by_global_norm (utils/optimization.py:233-237): g * clip / max(norm, clip)."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000003, generator=g) * 0.01
+    x = torch.cat([x, torch.zeros(1)])  # 16-byte friendly length not required
+    for clip in (0.5, 1e6):
+        gd = x.clone().to(DEV)
+        scratch = torch.zeros(1, dtype=torch.float64, device=DEV)
+        norm = torch.zeros(1, device=DEV)
+        ops.clip_by_global_norm(gd, clip, scratch, norm)
+        ref_norm = x.double().norm().item()
+        assert abs(float(norm) - ref_norm) < 1e-5 * ref_norm
+        ref = x * (clip / max(ref_norm, clip))
+        assert rel(gd, ref) < 1e-6

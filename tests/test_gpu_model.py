@@ -65,6 +65,8 @@ def test_pretrain_step_parity(tiny_cfg):
         om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)  # near-tie in attn sums
     for name in ("viz", "lang"):
         assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 1e-2  # rel-Frobenius, bf16 stacks
+    for k, v in om.attention_log.items():  # attention_log metrics (model/modeling.py:186-203)
+        assert abs(float(m.attention_log[k]) - float(v)) < 2e-3, k
     ll, linfo = m.mask_loss()
     cl, cinfo = m.contrastive_loss()
     tl, tinfo = m.temporal_loss(shuf.to(DEV), vid.to(DEV))
