@@ -325,8 +325,10 @@ static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL));
     attr_set = true;
   }
+  void* tok = gemm_prof_before(2.0 * (double)p.M * (double)p.N * (double)p.K, stream);
   MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM2_TOTAL, stream, ta, tb, to1, to2, p));
   MB_CHECK_LAUNCH();
+  gemm_prof_after(tok, stream);
   return MERLOT_OK;
 }
 

@@ -147,4 +147,8 @@ __device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int 
 }
 
 
+// bench.py roofline hook (gemm_tcgen05.cu): CUDA events around a K1 launch when profiling is switched on
+void* gemm_prof_before(double flops, cudaStream_t stream);
+void gemm_prof_after(void* tok, cudaStream_t stream);
+
 }  // namespace mb

@@ -270,6 +270,23 @@ struct ProfRec { cudaEvent_t e0, e1; double flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
+void* gemm_prof_before(double flops, cudaStream_t stream) {
+  if (!g_prof_on) return nullptr;
+  ProfRec* rec = new ProfRec;
+  rec->flops = flops;
+  cudaEventCreate(&rec->e0);
+  cudaEventCreate(&rec->e1);
+  cudaEventRecord(rec->e0, stream);
+  return rec;
+}
+void gemm_prof_after(void* tok, cudaStream_t stream) {
+  if (!tok) return;
+  ProfRec* rec = reinterpret_cast<ProfRec*>(tok);
+  cudaEventRecord(rec->e1, stream);
+  g_prof.push_back(*rec);
+  delete rec;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1, const CUtensorMap& to2,
                             const GemmDev& p, int grid, cudaStream_t stream) {
@@ -280,19 +297,10 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
-  ProfRec rec;
-  if (g_prof_on) {
-    MB_CHECK_CUDA(cudaEventCreate(&rec.e0));
-    MB_CHECK_CUDA(cudaEventCreate(&rec.e1));
-    rec.flops = 2.0 * (double)p.M * (double)p.N * (double)p.K;
-    MB_CHECK_CUDA(cudaEventRecord(rec.e0, stream));
-  }
+  void* tok = gemm_prof_before(2.0 * (double)p.M * (double)p.N * (double)p.K, stream);
   MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_TOTAL, stream, ta, tb, to1, to2, p));
   MB_CHECK_LAUNCH();
-  if (g_prof_on) {
-    MB_CHECK_CUDA(cudaEventRecord(rec.e1, stream));
-    g_prof.push_back(rec);
-  }
+  gemm_prof_after(tok, stream);
   return MERLOT_OK;
 }
 
