@@ -240,19 +240,49 @@ def run_ours(args):
     loss_val = spec.loss
 
     # ---- end to end: pinned host inputs, H2D inside the timed region, loss read back every step ----
+    # Every step copies ITS OWN inputs host->device (two device-side buffers; the copy of step i+1 runs on a copy stream while
+    # step i computes) and copies its three loss scalars device->pinned host memory; nothing blocks the host in between, all
+    # of it is inside the timed region and is drained before the clock stops.
     host = synthetic_batch(config, PER_GPU_BATCH, seed=rank + 1000, pin=True)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    for _ in range(2):
-        f = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        _ = one_step(f).loss
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    host_loss = torch.zeros(args.steps + 2, 3, dtype=torch.float32).pin_memory()
+
+    def start_copy(i):
+        j = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])  # the step that last read this buffer has finished with it
+            for k, v in host.items():
+                dev_bufs[j][k].copy_(v, non_blocking=True)
+            copied[j].record(copy_stream)
+
+    def e2e_step(i, slot):
+        j = i & 1
+        torch.cuda.current_stream().wait_event(copied[j])
+        spec = one_step(dev_bufs[j])
+        consumed[j].record(torch.cuda.current_stream())
+        host_loss[slot].copy_(torch.stack([x.reshape(()) for x in spec.loss_parts]), non_blocking=True)  # 12 bytes D2H
+
+    for j in range(2):
+        consumed[j].record(torch.cuda.current_stream())
+    start_copy(0)
+    for i in range(2):  # warm-up of this path
+        start_copy(i + 1)
+        e2e_step(i, args.steps + i)
     sync_all()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
-        f = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        loss_e2e = one_step(f).loss  # three fp32 scalars copied to the host
+    start_copy(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            start_copy(i + 1)
+        e2e_step(i, i)
     t1.record()
     sync_all()
+    loss_e2e = float(host_loss[args.steps - 1].sum())
     ms_e = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if dist is not None:
         dist.dist.all_reduce(ms_e, op=dist.dist.ReduceOp.MAX)
@@ -314,7 +344,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "loss": loss_val,
+            "loss": loss_val, "loss_e2e_last_step": loss_e2e,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
