@@ -303,6 +303,10 @@ int merlot_axpby_f32(const float* x, float* y, long long n, float a, float b, vo
  * end() synchronises the device and returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count. */
 void merlot_gemm_profile_begin(void);
 int merlot_gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
+/* kernel-tuning diagnostics: when buf (device, 8 x u64 per CTA, >= 8*148 entries) is non-null every 1-CTA K1 launch writes
+ * per-CTA stall cycles {total, mma:wait-smem-full, mma:wait-tmem-empty, tma:wait-smem-empty, epi:wait-tmem-full,
+ * epi:wait-staging, epi:work, tiles}.  Pass NULL to switch off (the default). */
+void merlot_gemm_debug_counters(void* buf_u64);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ constexpr int A2_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB: this CTA's 12
 constexpr int B2_BYTES = (BN2 / 2) * BLOCK_K * 2;        // 16 KB: this CTA's half of B
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr int STAGES2 = (SMEM_LIMIT - STAGING_BYTES) / STAGE2_BYTES;  // 6
-constexpr int SMEM2_TOTAL = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256;
+constexpr int SMEM2_TOTAL = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_SLOT_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -68,10 +68,10 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
                : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int FL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const __grid_constant__ CUtensorMap tma_o1, const __grid_constant__ CUtensorMap tma_o2, const GemmDev p) {
+                  const GemmDev p) {
   constexpr int BN = BN2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,6 +84,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint64_t* tmem_full = bars + 2 * STAGES2;        // per CTA, multicast commit
   uint64_t* tmem_empty = bars + 2 * STAGES2 + 2;   // leader only: both CTAs' epilogue warps arrive
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  float* bias_slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,7 +95,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (EPI != 0) { tma_prefetch_desc(&tma_o1); tma_prefetch_desc(&tma_o2); }
     for (int s = 0; s < STAGES2; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -195,8 +195,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int quad = warp & 3;
     const int half = e >> 2;
     const int row_in_tile = quad * 32 + lane;
-    const bool issuer = (e == 0 && lane == 0);
-    const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -237,75 +235,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
       } else {
-        const int pcols_max = (EPI == 2 || dual) ? 64 : 128;
-        const int phases = (BN + pcols_max - 1) / pcols_max;
-        for (int ph = 0; ph < phases; ++ph) {
-          if (issuer) tma_store_wait_read_all();
-          named_bar_sync(1, 32 * EPI_WARPS);
-          const int pcols = min(pcols_max, BN - ph * pcols_max);
-          const int wcols = pcols >> 1;
-          const int tcol0 = ph * pcols_max + half * wcols;
-#pragma unroll 1
-          for (int c = 0; c < wcols / 32; ++c) {
-            uint32_t r[32];
-            const int tcol = tcol0 + c * 32;
-            tmem_ld_32x32(taddr + tcol, r);
-            tmem_wait_ld();
-            const int col0 = n_blk * BN + tcol;
-            if (EPI == 2) {
-              uint8_t* box = staging + half * 16384;
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)g)) =
-                    make_uint4(__float_as_uint(__uint_as_float(r[g * 4 + 0]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 1]) * p.alpha),
-                               __float_as_uint(__uint_as_float(r[g * 4 + 2]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 3]) * p.alpha));
-            } else {
-              const int pcol = half * wcols + c * 32;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = col0 + g * 8;
-                float v[8], pre[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
-                const int chunk16 = ((pcol & 63) >> 3) + g;
-                if (dual) {
-                  stage_bf16x8(staging, row_in_tile, chunk16, pre);
-                  stage_bf16x8(staging + 16384, row_in_tile, chunk16, v);
-                } else {
-                  stage_bf16x8(staging + (pcol >> 6) * 16384, row_in_tile, chunk16, v);
-                }
-              }
-            }
-          }
-          if (ph == phases - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 32 * EPI_WARPS);
-          if (issuer) {
-            const int c0 = n_blk * BN + ph * pcols_max;
-            if (EPI == 2) {
-              for (int b2 = 0; b2 < 2; ++b2)
-                if (b2 * 32 < pcols && c0 + b2 * 32 < p.N) tma_reduce_add_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 32, row0);
-            } else if (dual) {
-              if (c0 < p.N) {
-                tma_store_2d(&tma_o1, staging, c0, row0);
-                tma_store_2d(&tma_o2, staging + 16384, c0, row0);
-              }
-            } else {
-              for (int b2 = 0; b2 < 2; ++b2)
-                if (b2 * 64 < pcols && c0 + b2 * 64 < p.N) tma_store_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 64, row0);
-            }
-            tma_store_commit();
-          }
-        }
+        epilogue_tile_loop<BN, EPI, FL>(p, FL == F_GENERIC ? epi_features(p) : FL, staging + e * 4096, bias_slots + e * 32, taddr, row0 + quad * 32, n_blk * BN, half, lane, [&] {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
+        });
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (EPI != 0 && issuer) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -316,34 +253,44 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1, const CUtensorMap& to2,
-                             const GemmDev& p, int grid, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI>;
+template <bool A_MN, bool B_MN, int EPI, int FL>
+static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t stream) {
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI, FL>;
   static bool attr_set = false;
   if (!attr_set) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL));
     attr_set = true;
   }
   void* tok = gemm_prof_before(2.0 * (double)p.M * (double)p.N * (double)p.K, stream);
-  MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM2_TOTAL, stream, ta, tb, to1, to2, p));
+  MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), SMEM2_TOTAL, stream, ta, tb, p));
   MB_CHECK_LAUNCH();
   gemm_prof_after(tok, stream);
   return MERLOT_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_gemm2_mn(int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t stream) {
+  if (epi == 0) return launch_gemm2_inst<A_MN, B_MN, 0, F_GENERIC>(ta, tb, p, grid, stream);
+  if (epi == 2) return launch_gemm2_inst<A_MN, B_MN, 2, F_ALPHA>(ta, tb, p, grid, stream);
+  switch (fl) {  // same specialised feature sets as the 1-CTA kernel (gemm_kernel.cuh)
+    case 0: return launch_gemm2_inst<A_MN, B_MN, 1, 0>(ta, tb, p, grid, stream);
+    case F_BIAS: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS>(ta, tb, p, grid, stream);
+    case F_BIAS | F_GELU | F_DUAL: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL>(ta, tb, p, grid, stream);
+    case F_DGELU: return launch_gemm2_inst<A_MN, B_MN, 1, F_DGELU>(ta, tb, p, grid, stream);
+    case F_BIAS | F_RESID: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_RESID>(ta, tb, p, grid, stream);
+    case F_BIAS | F_RESID | F_DROP: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_RESID | F_DROP>(ta, tb, p, grid, stream);
+    case F_RESID: return launch_gemm2_inst<A_MN, B_MN, 1, F_RESID>(ta, tb, p, grid, stream);
+    default: return launch_gemm2_inst<A_MN, B_MN, 1, F_GENERIC>(ta, tb, p, grid, stream);
+  }
+}
+
 // Called by merlot_gemm_bf16 when the pair kernel is selected.  `p` arrives with n_blocks for BN = 256.
-int launch_gemm_pair(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1,
-                     const CUtensorMap& to2, const GemmDev& p, int grid, cudaStream_t stream) {
-#define MB_G2(EPI_)                                                                                   \
-  if (a_mn && b_mn) return launch_gemm2_inst<true, true, EPI_>(ta, tb, to1, to2, p, grid, stream);    \
-  if (!a_mn && b_mn) return launch_gemm2_inst<false, true, EPI_>(ta, tb, to1, to2, p, grid, stream);  \
-  if (!a_mn && !b_mn) return launch_gemm2_inst<false, false, EPI_>(ta, tb, to1, to2, p, grid, stream); \
-  return launch_gemm2_inst<true, false, EPI_>(ta, tb, to1, to2, p, grid, stream);
-  if (epi == 1) { MB_G2(1) }
-  if (epi == 2) { MB_G2(2) }
-  MB_G2(0)
-#undef MB_G2
+int launch_gemm_pair(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+                     cudaStream_t stream) {
+  if (a_mn && b_mn) return launch_gemm2_mn<true, true>(epi, fl, ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm2_mn<false, true>(epi, fl, ta, tb, p, grid, stream);
+  if (!a_mn && !b_mn) return launch_gemm2_mn<false, false>(epi, fl, ta, tb, p, grid, stream);
+  return launch_gemm2_mn<true, false>(epi, fl, ta, tb, p, grid, stream);
 }
 
 }  // namespace mb

@@ -14,260 +14,10 @@
 
 namespace mb {
 
-// TS = true: bf16 outputs leave through 128B-swizzled smem staging boxes and TMA stores (fully coalesced, edge clipping
-// by the tensor map).  TS = false: direct register->global stores (fp32 outputs / atomics).
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_o1, const __grid_constant__ CUtensorMap tma_o2, const GemmDev p) {
-  using Cfg = GemmCfg<BN, EPI>;
-  constexpr bool TS = EPI != 0;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // 128B swizzle atoms need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (TS ? STAGING_BYTES : 0));
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    if (TS) { tma_prefetch_desc(&tma_o1); tma_prefetch_desc(&tma_o2); }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS);  // one arrival per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();  // everything above overlapped the previous kernel's tail
-
-  const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile % p.splits;
-        const int mn = tile / p.splits;
-        const int n_blk = mn % p.n_blocks;
-        const int m_blk = mn / p.n_blocks;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
-          uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
-          if (A_MN) {
-#pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d(sa + c * (BLOCK_K * 128), &tma_a, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
-          } else {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          }
-          if (B_MN) {
-#pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (BLOCK_K * 128), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BLOCK_K);
-          } else {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BLOCK_K, n_blk * BN);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile % p.splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t da = A_MN ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
-            const uint64_t db = B_MN ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ===================== epilogue warps (2 .. 2+EPI_WARPS) =====================
-    const int e = warp - 2;
-    const int quad = warp & 3;          // TMEM lane window this warp may touch: lanes [32*quad, 32*quad+32)
-    const int half = e >> 2;            // which half of the tile's columns this warp owns
-    const int row_in_tile = quad * 32 + lane;
-    const bool issuer = (e == 0 && lane == 0);
-    const bool dual = (p.flags & MERLOT_GEMM_GELU) && p.out2 != nullptr;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mn = tile / p.splits;
-      const int n_blk = mn % p.n_blocks;
-      const int m_blk = mn / p.n_blocks;
-      const int row = m_blk * BLOCK_M + row_in_tile;
-      const bool in_range = row < p.M;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      if (!TS) {
-        constexpr int CH = BN / 64;  // 32-column chunks per warp
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
-          uint32_t r[32];
-          const int tcol = half * (BN / 2) + c * 32;
-          tmem_ld_32x32(taddr + tcol, r);
-          tmem_wait_ld();
-          const int col0 = n_blk * BN + tcol;
-          if (in_range && col0 < p.N) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col < p.N) {
-                float v[8], pre[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                epi_math8(p, row, col, true, v, pre);
-                epi_store_direct(p, row, col, v, pre);
-              }
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      } else {
-        // Staged epilogue in phases of PCOLS accumulator columns; each phase fills the two 16 KB staging boxes
-        // ([128 rows][128 B], 128B-swizzled) and hands them to TMA:
-        //   bf16 single output : PCOLS = 128 -> box h = columns [64h, 64h+64) of the phase            (TMA store)
-        //   bf16 pre+act output: PCOLS = 64  -> box 0 = pre-activation, box 1 = gelu, same 64 columns  (2 TMA stores)
-        //   fp32 split-K accum : PCOLS = 64  -> box h = 32 fp32 columns                                (TMA reduce-add)
-        const int pcols_max = (EPI == 2 || dual) ? 64 : 128;
-        const int phases = (BN + pcols_max - 1) / pcols_max;
-        for (int ph = 0; ph < phases; ++ph) {
-          if (issuer) tma_store_wait_read_all();  // staging is free again
-          named_bar_sync(1, 32 * EPI_WARPS);
-          const int pcols = min(pcols_max, BN - ph * pcols_max);
-          const int wcols = pcols >> 1;           // columns per warp half: 64 or 32
-          const int tcol0 = ph * pcols_max + half * wcols;
-#pragma unroll 1
-          for (int c = 0; c < wcols / 32; ++c) {
-            uint32_t r[32];
-            const int tcol = tcol0 + c * 32;
-            tmem_ld_32x32(taddr + tcol, r);
-            tmem_wait_ld();
-            const int col0 = n_blk * BN + tcol;
-            if (EPI == 2) {
-              uint8_t* box = staging + half * 16384;
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)g)) =
-                    make_uint4(__float_as_uint(__uint_as_float(r[g * 4 + 0]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 1]) * p.alpha),
-                               __float_as_uint(__uint_as_float(r[g * 4 + 2]) * p.alpha), __float_as_uint(__uint_as_float(r[g * 4 + 3]) * p.alpha));
-            } else {
-              const int pcol = half * wcols + c * 32;  // column inside the phase
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = col0 + g * 8;
-                float v[8], pre[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                if (col < p.N) epi_math8(p, row, col, in_range, v, pre);
-                const int chunk16 = ((pcol & 63) >> 3) + g;
-                if (dual) {
-                  stage_bf16x8(staging, row_in_tile, chunk16, pre);
-                  stage_bf16x8(staging + 16384, row_in_tile, chunk16, v);
-                } else {
-                  stage_bf16x8(staging + (pcol >> 6) * 16384, row_in_tile, chunk16, v);
-                }
-              }
-            }
-          }
-          if (ph == phases - 1) {  // all TMEM reads of this accumulator stage are done
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 32 * EPI_WARPS);
-          if (issuer) {
-            const int r0 = m_blk * BLOCK_M;
-            const int c0 = n_blk * BN + ph * pcols_max;
-            if (EPI == 2) {
-              for (int b2 = 0; b2 < 2; ++b2)
-                if (b2 * 32 < pcols && c0 + b2 * 32 < p.N) tma_reduce_add_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 32, r0);
-            } else if (dual) {
-              if (c0 < p.N) {
-                tma_store_2d(&tma_o1, staging, c0, r0);
-                tma_store_2d(&tma_o2, staging + 16384, c0, r0);
-              }
-            } else {
-              for (int b2 = 0; b2 < 2; ++b2)
-                if (b2 * 64 < pcols && c0 + b2 * 64 < p.N) tma_store_2d(&tma_o1, staging + b2 * 16384, c0 + b2 * 64, r0);
-            }
-            tma_store_commit();
-          }
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (TS && issuer) tma_store_wait_all();  // global writes complete before the CTA exits
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
 // Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every GEMM launch.
 struct ProfRec { cudaEvent_t e0, e1; double flops; };
 static bool g_prof_on = false;
+static unsigned long long* g_dbg_counters = nullptr;
 static std::vector<ProfRec> g_prof;
 
 void* gemm_prof_before(double flops, cudaStream_t stream) {
@@ -287,28 +37,14 @@ void gemm_prof_after(void* tok, cudaStream_t stream) {
   delete rec;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1, const CUtensorMap& to2,
-                            const GemmDev& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EPI>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
-    attr_set = true;
-  }
-  void* tok = gemm_prof_before(2.0 * (double)p.M * (double)p.N * (double)p.K, stream);
-  MB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_TOTAL, stream, ta, tb, to1, to2, p));
-  MB_CHECK_LAUNCH();
-  gemm_prof_after(tok, stream);
-  return MERLOT_OK;
-}
-
 }  // namespace mb
 
 namespace mb {
-int launch_gemm_pair(bool a_mn, bool b_mn, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to1,
-                     const CUtensorMap& to2, const GemmDev& p, int grid, cudaStream_t stream);
+int launch_gemm_pair(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+                     cudaStream_t stream);
+template <int BN>
+int launch_gemm_bn(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+                   cudaStream_t stream);  // gemm_bn{128,192,256}.cu
 }
 
 using namespace mb;
@@ -332,8 +68,8 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   if (!out_f32)
     MB_REQUIRE((g->ld_out % 8) == 0 && ((uintptr_t)g->out % 16) == 0, MERLOT_ESHAPE,
                "gemm: bf16 output needs ld_out %% 8 == 0 and a 16-byte aligned base");
-  if (g->resid) MB_REQUIRE((g->ld_resid % 8) == 0, MERLOT_ESHAPE, "gemm: ld_resid %% 8 != 0");
-  if (g->aux) MB_REQUIRE((g->ld_aux % 8) == 0, MERLOT_ESHAPE, "gemm: ld_aux %% 8 != 0");
+  if (g->resid) MB_REQUIRE((g->ld_resid % 8) == 0 && ((uintptr_t)g->resid % 16) == 0, MERLOT_ESHAPE, "gemm: resid needs ld_resid %% 8 == 0 and a 16-byte aligned base");
+  if (g->aux) MB_REQUIRE((g->ld_aux % 8) == 0 && ((uintptr_t)g->aux % 16) == 0, MERLOT_ESHAPE, "gemm: aux needs ld_aux %% 8 == 0 and a 16-byte aligned base");
   if (g->out2) MB_REQUIRE((g->ld_out2 % 8) == 0, MERLOT_ESHAPE, "gemm: ld_out2 %% 8 != 0");
   if (g->flags & MERLOT_GEMM_DROPOUT)
     MB_REQUIRE((g->N % 8) == 0 && g->dropout_p >= 0.f && g->dropout_p < 1.f, MERLOT_ESHAPE,
@@ -357,6 +93,7 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
     p.flags &= ~MERLOT_GEMM_DROPOUT;
   }
 
+  p.dbg = g_dbg_counters;
   const int sms = num_sms();
   p.m_blocks = ceil_div(g->M, BLOCK_M);
   p.num_kb = ceil_div(g->K, BLOCK_K);
@@ -425,37 +162,18 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   const bool plain = !g->bias && !g->resid && !(g->flags & (MERLOT_GEMM_GELU | MERLOT_GEMM_MUL_DGELU | MERLOT_GEMM_DROPOUT));
   const int epi = !out_f32 ? 1
                   : ((g->flags & MERLOT_GEMM_ATOMIC) && plain && (g->ld_out % 4) == 0 && ((uintptr_t)g->out % 16) == 0) ? 2 : 0;
-  CUtensorMap to1, to2;
-  memset(&to1, 0, sizeof(to1));
-  memset(&to2, 0, sizeof(to2));
-  if (epi == 1) {
-    const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
-    if (dual) MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
-    rc = make_tmap_bf16_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 64, BLOCK_M);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&to2, dual ? g->out2 : g->out, (uint64_t)g->N, (uint64_t)g->M,
-                           (uint64_t)(dual ? g->ld_out2 : g->ld_out), 64, BLOCK_M);
-    if (rc) return rc;
-  } else if (epi == 2) {
-    rc = make_tmap_f32_2d(&to1, g->out, (uint64_t)g->N, (uint64_t)g->M, (uint64_t)g->ld_out, 32, BLOCK_M);
-    if (rc) return rc;
-  }
-  if (pair) return launch_gemm_pair(g->a_mn_major != 0, g->b_mn_major != 0, epi, ta, tb, to1, to2, p, grid, stream);
-#define MB_GEMM_DISPATCH2(BN_, EPI_)                                                                                  \
-  if (g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, true, true, EPI_>(ta, tb, to1, to2, p, grid, stream);   \
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm_inst<BN_, false, true, EPI_>(ta, tb, to1, to2, p, grid, stream); \
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm_inst<BN_, false, false, EPI_>(ta, tb, to1, to2, p, grid, stream); \
-  return launch_gemm_inst<BN_, true, false, EPI_>(ta, tb, to1, to2, p, grid, stream);
-#define MB_GEMM_DISPATCH(BN_)                  \
-  if (epi == 1) { MB_GEMM_DISPATCH2(BN_, 1) }  \
-  if (epi == 2) { MB_GEMM_DISPATCH2(BN_, 2) }  \
-  MB_GEMM_DISPATCH2(BN_, 0)
-  if (bn == 256) { MB_GEMM_DISPATCH(256) }
-  if (bn == 192) { MB_GEMM_DISPATCH(192) }
-  MB_GEMM_DISPATCH(128)
-#undef MB_GEMM_DISPATCH
-#undef MB_GEMM_DISPATCH2
+  const int fl = (p.alpha != 1.0f ? F_ALPHA : 0) | (p.bias ? F_BIAS : 0) | ((p.flags & MERLOT_GEMM_GELU) ? F_GELU : 0) |
+                 (((p.flags & MERLOT_GEMM_GELU) && p.out2) ? F_DUAL : 0) | ((p.flags & MERLOT_GEMM_MUL_DGELU) ? F_DGELU : 0) |
+                 ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0);
+  if (epi == 1 && (g->flags & MERLOT_GEMM_GELU) && g->out2)
+    MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
+  if (pair) return launch_gemm_pair(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
+  if (bn == 256) return launch_gemm_bn<256>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
+  if (bn == 192) return launch_gemm_bn<192>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
+  return launch_gemm_bn<128>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
 }
+
+extern "C" void merlot_gemm_debug_counters(void* buf_u64) { g_dbg_counters = reinterpret_cast<unsigned long long*>(buf_u64); }
 
 extern "C" void merlot_gemm_profile_begin(void) {
   for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
