@@ -198,6 +198,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const uint32_t leader_tmem_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int rtf = FL == F_GENERIC ? epi_features(p) : FL;
+    EpiCarry cy;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int mn = tile / p.splits;
       const int n_blk = mn % p.n_blocks;
@@ -205,6 +207,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int row0 = m2 * 256 + (int)rank * BLOCK_M;
       const int row = row0 + row_in_tile;
       const bool in_range = row < p.M;
+      if (EPI != 0) epilogue_prefetch<BN, EPI, FL>(p, rtf, row0 + quad * 32, n_blk * BN, half, lane, cy);  // hidden by the wait
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
@@ -235,7 +238,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);
       } else {
-        epilogue_tile_loop<BN, EPI, FL>(p, FL == F_GENERIC ? epi_features(p) : FL, staging + e * 4096, bias_slots + e * 32, taddr, row0 + quad * 32, n_blk * BN, half, lane, [&] {
+        epilogue_tile_loop<BN, EPI, FL>(p, rtf, staging + e * 4096, bias_slots + e * 32, taddr, row0 + quad * 32, n_blk * BN, half, lane, cy, [&] {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + acc * 8);

@@ -254,61 +254,91 @@ static __device__ __noinline__ void store_bf16_tail(bf16* o, uint4 q, int n) {  
 //     parked in the slot, read back by the owning thread and overwritten in place by the result.
 // `release()` is called by the whole warp once the last tcgen05.ld of the tile has completed (TMEM stage reusable).
 // ---------------------------------------------------------------------------------------------------------------------
+// Operands fetched ahead of their use and carried from one tile's epilogue into the next (registers; the tile loop is inlined)
+struct EpiCarry {
+  uint4 cp[8];  // companion block of the next 64-column unit
+  float bnext;  // bias value of column (next chunk) + lane
+};
+
+template <int BN, int EPI, int FL>
+struct EpiPlan {  // which chunks / columns an epilogue warp walks (depends only on the feature set and the warp's half)
+  bool dual, wide;
+  int half, my_chunks;
+  __device__ __forceinline__ EpiPlan(int rtf, int half_) : half(half_) {
+    dual = EPI == 1 && feat<FL>(rtf, F_DUAL);
+    wide = EPI == 1 && !dual;
+    constexpr int NU0 = (BN / 64 + 1) / 2;  // 64-column units of half 0 (half 1 owns BN/64 - NU0)
+    my_chunks = wide ? 2 * (half == 0 ? NU0 : BN / 64 - NU0) : BN / 64;
+  }
+  __device__ __forceinline__ int tcol_of(int i) const { return wide ? ((2 * (i >> 1) + half) * 2 + (i & 1)) * 32 : (2 * i + half) * 32; }
+};
+
+template <int BN, int EPI, int FL>
+__device__ __forceinline__ void epilogue_prefetch(const GemmDev& p, int rtf, int row0q, int n0, int half, int lane, EpiCarry& cy) {
+  const EpiPlan<BN, EPI, FL> plan(rtf, half);
+  if (EPI == 1 && feat<FL>(rtf, F_BIAS)) {
+    const int c = n0 + plan.tcol_of(0) + lane;
+    cy.bnext = c < p.N ? __ldg(p.bias + c) : 0.0f;
+  }
+  if (plan.wide && (feat<FL>(rtf, F_DGELU) || feat<FL>(rtf, F_RESID))) {
+    const bool dg = feat<FL>(rtf, F_DGELU);
+    comp_fetch(dg ? p.aux : p.resid, dg ? p.ld_aux : p.ld_resid, row0q, n0 + plan.tcol_of(0), p.M, p.N, lane, cy.cp);
+  }
+}
+
+// One tile.  `cy` holds the operands prefetched for this tile's first chunk (epilogue_prefetch, issued by the caller before it
+// waits for the accumulator so that the wait hides their latency).
 template <int BN, int EPI, int FL, typename Release>
-__device__ __forceinline__ void epilogue_tile_loop(const GemmDev& p, int rtf, uint8_t* slot, float* bias_slot, uint32_t taddr, int row0q, int n0, int half, int lane,
-                                                     Release&& release) {
+__device__ __forceinline__ void epilogue_tile_loop(const GemmDev& p, int rtf, uint8_t* slot, float* bias_slot, uint32_t taddr, int row0q, int n0,
+                                                   int half, int lane, EpiCarry& cy, Release&& release) {
+  // the slots are shared memory; without the hint the pointers (through the lambda/struct plumbing) compile to generic LD.E/ST.E
+  __builtin_assume(__isShared(slot));
+  __builtin_assume(__isShared(bias_slot));
   // EPI 1, single output: 64-column units of two chunks (unit index 2*j + half).  Dual output and fp32: one 32-column chunk per
   // unit (index 2*i + half); the dual slot row is [pre 64 B | act 64 B].
   // The chunk loop is deliberately NOT unrolled (one copy of the math body): a fully unrolled epilogue is 20k instructions and
   // thrashes the instruction cache (measured 2.5x slower).  The accumulator double buffer is a register copy instead.
-  const bool dual = EPI == 1 && feat<FL>(rtf, F_DUAL);
-  const bool wide = EPI == 1 && !dual;
-  constexpr int NU0 = (BN / 64 + 1) / 2;  // 64-column units of half 0 (half 1 owns BN/64 - NU0)
-  const int my_chunks = wide ? 2 * (half == 0 ? NU0 : BN / 64 - NU0) : BN / 64;
+  const EpiPlan<BN, EPI, FL> plan(rtf, half);
+  const bool dual = plan.dual, wide = plan.wide;
+  const int my_chunks = plan.my_chunks;
   const int row = row0q + lane;
   const bool in_range = row < p.M;
   const bool do_dgelu = feat<FL>(rtf, F_DGELU);
   const bf16* comp = !wide ? nullptr : do_dgelu ? p.aux : (feat<FL>(rtf, F_RESID) ? p.resid : nullptr);
   const int ld_comp = do_dgelu ? p.ld_aux : p.ld_resid;
   const bf16* resid2 = ((!wide || do_dgelu) && feat<FL>(rtf, F_RESID)) ? p.resid + (size_t)row * p.ld_resid : nullptr;  // rare: unprefetched
-  auto tcol_of = [&](int i) { return wide ? ((2 * (i >> 1) + half) * 2 + (i & 1)) * 32 : (2 * i + half) * 32; };
-  uint32_t rn[32], rc[32];
-  uint4 cp[8];
   const bool has_bias = EPI == 1 && feat<FL>(rtf, F_BIAS);
-  auto bias_fetch = [&](int i) {  // one coalesced 128-byte load per chunk, a chunk ahead of its use
-    const int c = n0 + tcol_of(i) + lane;
-    return c < p.N ? __ldg(p.bias + c) : 0.0f;
-  };
-  float bnext = 0.0f;
-  tmem_ld_32x32(taddr + (uint32_t)tcol_of(0), rn);
-  if (has_bias) bnext = bias_fetch(0);
-  if (comp) comp_fetch(comp, ld_comp, row0q, n0 + tcol_of(0), p.M, p.N, lane, cp);
+  uint32_t rn[32], rc[32];
+  tmem_ld_32x32(taddr + (uint32_t)plan.tcol_of(0), rn);
 #pragma unroll 1
   for (int i = 0; i < my_chunks; ++i) {
-    const int tcol = tcol_of(i);
+    const int tcol = plan.tcol_of(i);
     const int col0 = n0 + tcol;
     const int sub = wide ? (i & 1) : 0;
-    const int ucol0 = wide ? n0 + tcol_of(i & ~1) : col0;  // first column of the unit
-    const bool live = ucol0 < p.N;                         // unit not entirely right of the matrix (warp-uniform)
-    if (comp && sub == 0 && live) {
-      // park the companion block in the slot, then start fetching the next unit's
+    const int ucol0 = wide ? n0 + plan.tcol_of(i & ~1) : col0;  // first column of the unit
+    const bool live = ucol0 < p.N;                              // unit not entirely right of the matrix (warp-uniform)
+    if (comp && sub == 0) {
+      // park the companion block in the slot, then start fetching the next unit's (or the next tile's first)
+      if (live) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<uint4*>(slot + sw128_offset((uint32_t)(k * 4 + (lane >> 3)), (uint32_t)(lane & 7))) = cp[k];
-      if (i + 2 < my_chunks) comp_fetch(comp, ld_comp, row0q, n0 + tcol_of(i + 2), p.M, p.N, lane, cp);
+        for (int k = 0; k < 8; ++k)
+          *reinterpret_cast<uint4*>(slot + sw128_offset((uint32_t)(k * 4 + (lane >> 3)), (uint32_t)(lane & 7))) = cy.cp[k];
+      }
+      if (i + 2 < my_chunks) comp_fetch(comp, ld_comp, row0q, n0 + plan.tcol_of(i + 2), p.M, p.N, lane, cy.cp);
       __syncwarp();
     }
     if (has_bias) {
       __syncwarp();  // the chunk before has finished reading the slot
-      bias_slot[lane] = bnext;
+      bias_slot[lane] = cy.bnext;
       __syncwarp();
-      if (i + 1 < my_chunks) bnext = bias_fetch(i + 1);
+      const int c = n0 + plan.tcol_of(i + 1) + lane;
+      cy.bnext = (i + 1 < my_chunks && c < p.N) ? __ldg(p.bias + c) : 0.0f;
     }
     tmem_wait_ld_regs(rn);
 #pragma unroll
     for (int k = 0; k < 32; ++k) rc[k] = rn[k];
     if (i + 1 < my_chunks) {
-      tmem_ld_32x32(taddr + (uint32_t)tcol_of(i + 1), rn);
+      tmem_ld_32x32(taddr + (uint32_t)plan.tcol_of(i + 1), rn);
     } else {
       release();
     }
@@ -386,7 +416,6 @@ __device__ __forceinline__ void epilogue_tile_loop(const GemmDev& p, int rtf, ui
     }
   }
 }
-
 
 // bench.py roofline hook (gemm_tcgen05.cu): CUDA events around a K1 launch when profiling is switched on
 void* gemm_prof_before(double flops, cudaStream_t stream);

@@ -150,6 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int rtf = FL == F_GENERIC ? epi_features(p) : FL;
     long long w_tfull = 0, w_stage = 0, w_work = 0;
     const bool dbg = p.dbg != nullptr && e == 0 && lane == 0;
+    EpiCarry cy;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
       const int n_blk = mn % p.n_blocks;
@@ -157,6 +158,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int row = m_blk * BLOCK_M + row_in_tile;
       const bool in_range = row < p.M;
       long long t0 = dbg ? clock64() : 0;
+      if (EPI != 0) epilogue_prefetch<BN, EPI, FL>(p, rtf, m_blk * BLOCK_M + quad * 32, n_blk * BN, half, lane, cy);  // hidden by the wait
       mbar_wait(&tmem_full[acc], acc_phase);
       if (dbg) { const long long t1 = clock64(); w_tfull += t1 - t0; t0 = t1; }
       tc_fence_after();
@@ -188,8 +190,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       } else {
-        epilogue_tile_loop<BN, EPI, FL>(p, rtf, staging + e * 4096, bias_slots + e * 32, taddr, m_blk * BLOCK_M + quad * 32, n_blk * BN, half, lane,
-                                      [&] {
+        epilogue_tile_loop<BN, EPI, FL>(p, rtf, staging + e * 4096, bias_slots + e * 32, taddr, m_blk * BLOCK_M + quad * 32, n_blk * BN, half,
+                                      lane, cy, [&] {
                                         tc_fence_before();
                                         __syncwarp();
                                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
