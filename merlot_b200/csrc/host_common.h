@@ -1,6 +1,7 @@
 // Host-side helpers shared by all translation units of libmerlot_b200.so:
 // error reporting (C-ABI returns int codes + thread-local message), launch counting, TMA tensor-map encoding.
 #pragma once
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,7 +60,8 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  static const bool no_pdl = [] { const char* e = getenv("MERLOT_NO_PDL"); return e && e[0] == '1'; }();  // diagnostics: true per-kernel times
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

@@ -210,20 +210,19 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 //   partial[block] = { sum dy*xhat, sum dy, sum dmask }   (dgamma, dbeta, and the bias gradient of the next linear)
 // x and dy stay packed (bf16x2) in registers between the two sweeps so 2 blocks of 8 warps fit per SM.
 // -----------------------------------------------------------------------------------------------------------------
+constexpr int LNF_WARPS = 12;  // one block of 12 warps per SM: the column partials meet in smem, one red.add set per block
 template <int NCH>  // 16-byte chunks per lane: NCH = ceil(H / 256), H % 8 == 0 (H = 768 -> NCH = 3)
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(32 * LNF_WARPS, 1)
 ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
                     bf16* __restrict__ dx, bf16* __restrict__ dmask, float* __restrict__ out_g, float* __restrict__ out_b,
                     float* __restrict__ out_bias, long long rows, int H, int want_bias,
                     uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
-  extern __shared__ float sred[];  // [3][H]
+  extern __shared__ float sred[];  // [LNF_WARPS][3][H]: every warp's column partials (dgamma | dbeta | bias)
   pdl_launch_dependents();
   const int nchunk = H >> 3;
   const float invH = 1.0f / (float)H;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
   pdl_wait();
   float dg[NCH][8], db[NCH][8], bs[NCH][8];
 #pragma unroll
@@ -307,23 +306,31 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
       }
     }
   }
+  // warp partials -> smem (plain stores, each warp its own [3][H] slab), summed over the warps by the whole block, then ONE
+  // red.global.add per column and block (the same-address reductions of many small blocks used to be the kernel's fixed cost)
+  float* mine = sred + (size_t)warp * 3 * H;
 #pragma unroll
   for (int j = 0; j < NCH; ++j) {
     const int c = (lane + 32 * j) * 8;
     if (lane + 32 * j >= nchunk) continue;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sred[c + i], dg[j][i]);
-      atomicAdd(&sred[H + c + i], db[j][i]);
-      if (want_bias) atomicAdd(&sred[2 * H + c + i], bs[j][i]);
+    *reinterpret_cast<float4*>(mine + c) = make_float4(dg[j][0], dg[j][1], dg[j][2], dg[j][3]);
+    *reinterpret_cast<float4*>(mine + c + 4) = make_float4(dg[j][4], dg[j][5], dg[j][6], dg[j][7]);
+    *reinterpret_cast<float4*>(mine + H + c) = make_float4(db[j][0], db[j][1], db[j][2], db[j][3]);
+    *reinterpret_cast<float4*>(mine + H + c + 4) = make_float4(db[j][4], db[j][5], db[j][6], db[j][7]);
+    if (want_bias) {
+      *reinterpret_cast<float4*>(mine + 2 * H + c) = make_float4(bs[j][0], bs[j][1], bs[j][2], bs[j][3]);
+      *reinterpret_cast<float4*>(mine + 2 * H + c + 4) = make_float4(bs[j][4], bs[j][5], bs[j][6], bs[j][7]);
     }
   }
   __syncthreads();
-  // block partials -> fp32 red.add straight into the gradient arena (dgamma | dbeta | bias)
   for (int i4 = threadIdx.x * 4; i4 < (want_bias ? 3 : 2) * H; i4 += blockDim.x * 4) {  // H % 8 == 0: a float4 never straddles
+    float4 a = *reinterpret_cast<const float4*>(sred + i4);
+    for (int w = 1; w < nwarp; ++w) {
+      const float4 b = *reinterpret_cast<const float4*>(sred + (size_t)w * 3 * H + i4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
     float* dst = i4 < H ? out_g + i4 : (i4 < 2 * H ? out_b + (i4 - H) : out_bias + (i4 - 2 * H));
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sred[i4]), "f"(sred[i4 + 1]), "f"(sred[i4 + 2]),
-                 "f"(sred[i4 + 3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
   }
 }
 
@@ -641,14 +648,22 @@ extern "C" int merlot_layernorm_bwd_fused(const void* dy, const void* x, const f
   if (rows == 0) return MERLOT_OK;
   const uint32_t th = dropout_p > 0.f ? thresh16(dropout_p) : 0;
   const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-  long long want = ceil_div_ll(rows, 4);
-  const int grid = (int)(want < 3 * 148 ? want : 3 * 148);
-  const size_t smem = (size_t)3 * H * sizeof(float);
+  long long want = ceil_div_ll(rows, LNF_WARPS);
+  const int sms = num_sms();
+  const int grid = (int)(want < sms ? want : sms);
+  const size_t smem = (size_t)LNF_WARPS * 3 * H * sizeof(float);
   (void)workspace;
 #define LNF(N_)                                                                                                          \
-  MB_CHECK_CUDA(launch_pdl(ln_bwd_fused_kernel<N_>, dim3(grid), dim3(128), smem, st, (const bf16*)dy, (const bf16*)x, mean, rstd, \
-                           gamma, (const bf16*)dres, (bf16*)dx, (bf16*)dmask, dgamma, dbeta, dbias, rows, H,           \
-                           (int)(dbias != nullptr), th, sc, seed, site))
+  do {                                                                                                                   \
+    static bool attr_set = false;                                                                                        \
+    if (!attr_set) {                                                                                                     \
+      MB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_fused_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNF_WARPS * 3 * 1024 * 4)); \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    MB_CHECK_CUDA(launch_pdl(ln_bwd_fused_kernel<N_>, dim3(grid), dim3(32 * LNF_WARPS), smem, st, (const bf16*)dy, (const bf16*)x, mean, \
+                             rstd, gamma, (const bf16*)dres, (bf16*)dx, (bf16*)dmask, dgamma, dbeta, dbias, rows, H,     \
+                             (int)(dbias != nullptr), th, sc, seed, site));                                              \
+  } while (0)
   if (H <= 256) LNF(1); else if (H <= 512) LNF(2); else if (H <= 768) LNF(3); else LNF(4);
 #undef LNF
   MB_CHECK_LAUNCH();

@@ -29,8 +29,13 @@ print(f"kernels={len(evs)} span={span / 1e3:.3f} ms busy={busy / 1e3:.3f} ms idl
       f"(mean gap {sum(pos) / max(1, len(pos)):.2f} us, gaps>5us: {sum(1 for g in pos if g > 5)})  [2 steps]")
 agg = defaultdict(lambda: [0, 0.0])
 for e in evs:
-    n = e.name.split("(")[0].replace("void ", "")
+    n = e.name
+    if ">(" in n:
+        n = n[: n.rindex(">(") + 1]
+    else:
+        n = n.split("(")[0]
+    n = n.replace("void ", "").replace("(int)", "").replace("(bool)", "").replace("mb::", "")
     agg[n][0] += 1
     agg[n][1] += e.time_range.end - e.time_range.start
-for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{us / 2e3:8.3f} ms/step  n={n // 2:4d}  avg={us / n:7.1f} us  {k[:90]}")
