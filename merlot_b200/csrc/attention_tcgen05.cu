@@ -119,17 +119,20 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   const float sc2 = vq ? p.scale * LOG2E : 0.f;
   float m_used = -INFINITY, l_run = 0.f;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(AT_M, AT_N, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
 
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
     const int k0 = j * AT_N;
+    // a ragged last key tile (S = 266: 10 keys) only costs its 32-key chunks: S = Q K^T with N = 32 nck, nck chunks of
+    // softmax, 2 nck k16-steps of P V
+    const int nck = min(AT_N / 32, (S - k0 + 31) >> 5);
     if (tid == 0) {
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(bar_k, ph);
       tc_fence_after();
       const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+      const uint32_t idesc_s = make_idesc_bf16(AT_M, nck * 32, 0, 0);
 #pragma unroll
       for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
       umma_commit(bar_s);
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
+      if (c >= nck) break;
       uint32_t r[32];
       tmem_ld_32x32(tS + lane_off + c * 32, r);
       tmem_wait_ld();
@@ -188,6 +192,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     float rowsum = 0.f;
 #pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
+      if (c >= nck) break;
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
       const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
       for (int k = 0; k < AT_N / 16; ++k) {
+        if (k >= 2 * nck) break;
         const uint64_t da = desc_kmajor(pa + (k >> 2) * 16384, k & 3);
         const uint64_t db = desc_mnmajor(va, k, 0);  // single 64-wide chunk: LBO unused
         umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
@@ -316,7 +322,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
   const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
-  constexpr uint32_t idesc_st = make_idesc_bf16(AT_N, AT_M, 0, 0);   // S^T, dP^T : both operands K-major (d)
+  // a ragged last query tile only costs its 32-query chunks (S^T / dP^T with N = 32 ncq, ncq softmax chunks, 2 ncq k16-steps
+  // of dV / dK); dQ keeps its 128 rows (TMEM lanes) -- the rows past S are computed from stale dS^T columns and never stored
+  auto ncq_of = [&](int i) { return min(AT_M / 32, (S - i * AT_M + 31) >> 5); };
   constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
   constexpr uint32_t idesc_dq = make_idesc_bf16(AT_M, AT_D, 1, 1);   // A = dS (MN-major view of dS^T), B = K MN-major
 
@@ -330,6 +338,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_wait(&bar_q[i & 1], (uint32_t)((i >> 1) & 1));
     tc_fence_after();
     const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQd + (i & 1) * 32768), da = qa + 16384;
+    const uint32_t idesc_st = make_idesc_bf16(AT_N, ncq_of(i) * 32, 0, 0);  // S^T, dP^T : both operands K-major (d)
 #pragma unroll
     for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
 #pragma unroll
@@ -356,10 +365,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int q0 = i * AT_M;
     const float* nlse = s_nlse + (i & 1) * 128;
     const float* dsm = s_dsum + (i & 1) * 128;
+    const int ncq = ncq_of(i);
     mbar_wait(bar_1, ph);
     tc_fence_after();
 #pragma unroll 1
     for (int c = wg * 2; c < wg * 2 + 2; ++c) {
+      if (c >= ncq) break;  // warp-uniform
       uint32_t rs[32], rd[32];
       tmem_ld_32x32(tST + lane_off + c * 32, rs);
       tmem_ld_32x32(tdPT + lane_off + c * 32, rd);
@@ -406,10 +417,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                      ka = smem_u32(sK);
 #pragma unroll
       for (int k = 0; k < AT_M / 16; ++k)  // dV += P^T dO   (contraction over q)
-        umma_bf16_ss(tdV, desc_kmajor(pa + (k >> 2) * 16384, k & 3), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
+        if (k < 2 * ncq) umma_bf16_ss(tdV, desc_kmajor(pa + (k >> 2) * 16384, k & 3), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
 #pragma unroll
       for (int k = 0; k < AT_M / 16; ++k)  // dK += dS^T Q
-        umma_bf16_ss(tdK, desc_kmajor(sa + (k >> 2) * 16384, k & 3), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
+        if (k < 2 * ncq) umma_bf16_ss(tdK, desc_kmajor(sa + (k >> 2) * 16384, k & 3), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
 #pragma unroll
       for (int k = 0; k < AT_N / 16; ++k)  // dQ_i = dS K      (contraction over keys; A = MN-major view of dS^T)
         umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 16384), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);

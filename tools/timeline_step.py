@@ -23,8 +23,12 @@ evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CU
 evs.sort(key=lambda e: e.time_range.start)
 span = evs[-1].time_range.end - evs[0].time_range.start
 busy = sum(e.time_range.end - e.time_range.start for e in evs)
-gaps = [evs[i + 1].time_range.start - evs[i].time_range.end for i in range(len(evs) - 1)]
-pos = [g for g in gaps if g > 0]
+# idle = span minus the UNION of the kernel intervals (PDL / side-stream kernels overlap, so a plain sum double-counts)
+pos, cur_end = [], evs[0].time_range.end
+for e in evs[1:]:
+    if e.time_range.start > cur_end:
+        pos.append(e.time_range.start - cur_end)
+    cur_end = max(cur_end, e.time_range.end)
 print(f"kernels={len(evs)} span={span / 1e3:.3f} ms busy={busy / 1e3:.3f} ms idle={sum(pos) / 1e3:.3f} ms "
       f"(mean gap {sum(pos) / max(1, len(pos)):.2f} us, gaps>5us: {sum(1 for g in pos if g > 5)})  [2 steps]")
 agg = defaultdict(lambda: [0, 0.0])
