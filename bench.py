@@ -309,8 +309,12 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": ach / sustained, "traffic": None, "peak_source": f"{how} bf16_tflops_sustained",
                 "launches_per_step": nl.value, "gemm_ms_per_step": tm.value, "gemm_share_of_step": tm.value / (ms_total / args.steps),
                 "note": "sum over all K1 launches (1-CTA and CTA-pair variants) of one single-stream step: sum(2MNK) / sum(CUDA-event "
-                        "duration on the launch stream); isolated large-shape rates are in profiles/"}
+                        "duration on the launch stream). The event pairs switch off the PDL overlap between consecutive kernels and "
+                        "add ~2 us per launch, so this is a lower bound (CUPTI kernel times give ~9.5 ms of K1 per step); isolated "
+                        "per-shape rates are in profiles/r01_k1_epilogue_timings.txt"}
     torch.cuda.synchronize()
+    # ---- attention TFLOP/s as a share of the peak (second half of BASELINE.json's metric), rank 0, after the timed regions ----
+    attn = attention_rates(dev) if rank == 0 else None
     if dist is not None:
         dist.barrier()
 
@@ -343,12 +347,48 @@ def run_ours(args):
                     "ms_per_step": float(ms_e) / args.steps},
             "gpu_launches": launches,
             "roofline": roof,
+            "attention": attn,
             "cpu_baseline": cpu,
             "loss": loss_val, "loss_e2e_last_step": loss_e2e,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+
+
+def attention_rates(dev):
+    """K2 (forward) and K3 (backward incl. dsum / dq finish) alone, CUDA-event timed, at the ViT shape of configs[1]
+    (32 frames x 266 tokens) and the joint-encoder shape of SURVEY 8(d) cfg5 (16 x 3608 tokens, key mask off); algorithmic
+    FLOPs 4 B h S^2 d forward, 10 B h S^2 d backward (all S keys, no mask discount)."""
+    from merlot_b200 import ops
+    sustained, _, _, how = peaks()
+    out = {"peak": sustained, "peak_source": f"{how} bf16_tflops_sustained", "unit": "TFLOP/s", "shapes": {}}
+    g = torch.Generator().manual_seed(0)
+    for name, (B, S, it) in {"cfg2_vit_B32_S266": (32, 266, 10), "cfg5_joint_B16_S3608": (16, 3608, 3)}.items():
+        heads, H = 12, 768
+        qkv = (torch.randn(B * S, 3 * H, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        dctx = (torch.randn(B * S, H, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+        ctx, lse = ops.attention_fwd(qkv, B, S, heads)
+        dqkv = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=dev)
+        dq_acc = torch.zeros(B * S, H, dtype=torch.float32, device=dev)  # K3 hands it back zeroed
+        dsum = torch.empty(B, heads, S, dtype=torch.float32, device=dev)
+        ops.attention_bwd(qkv, ctx, dctx, lse, B, S, heads, dqkv=dqkv, dq_accum=dq_acc, dsum=dsum)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(it):
+            ops.attention_fwd(qkv, B, S, heads, ctx=ctx, lse=lse)
+        ev[1].record()
+        for _ in range(it):
+            ops.attention_bwd(qkv, ctx, dctx, lse, B, S, heads, dqkv=dqkv, dq_accum=dq_acc, dsum=dsum)
+        ev[2].record()
+        torch.cuda.synchronize()
+        f = 4.0 * B * heads * S * S * 64
+        tf_f = f / (ev[0].elapsed_time(ev[1]) / it * 1e-3) / 1e12
+        tf_b = 2.5 * f / (ev[1].elapsed_time(ev[2]) / it * 1e-3) / 1e12
+        out["shapes"][name] = {"fwd_tflops": tf_f, "bwd_tflops": tf_b, "fwd_frac": tf_f / sustained, "bwd_frac": tf_b / sustained}
+        del qkv, dctx, ctx, lse, dqkv, dq_acc, dsum
+    return out
 
 
 def main():
