@@ -52,7 +52,7 @@ __device__ __forceinline__ float masked_score(float s, float sc2, bool vq, bool 
 // The running maximum is only advanced when it grows by more than 2^8 (lazy rescale: O is then corrected in TMEM with
 // tcgen05.ld/st), so the common iteration never touches O.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = 16384 * 3 + 32768 + 1024 + 1024;
+constexpr int FWD_SMEM = 16384 * 4 + 32768 + 1024 + 1024;  // Q, K, 2 x V, P, masks + barriers
 constexpr int MAX_MASK_WORDS = 128;  // key-validity bitmask for up to 4096 keys
 constexpr float MASKED_LOG2 = -1e10f * LOG2E;
 
@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;
-  uint8_t* sV = smem + 32768;
-  uint8_t* sP = smem + 49152;  // [128 q rows][128 keys] bf16, two 64-key K-major atoms of 16 KB
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 49152 + 32768);  // [MAX_MASK_WORDS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 32768 + 512);
-  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2, *bar_s = bars + 3, *bar_o = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* sV = smem + 32768;  // two V tiles: tile j lives in buffer j & 1 (loaded a whole tile ahead)
+  uint8_t* sP = smem + 65536;  // [128 q rows][128 keys] bf16, two 64-key K-major atoms of 16 KB
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 65536 + 32768);  // [MAX_MASK_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 32768 + 512);
+  uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_o = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
-    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
     mbar_arrive_expect_tx(bar_k, 16384);
     tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0);
-    mbar_arrive_expect_tx(bar_v, 16384);
-    tma_load_2d(sV, &tm_qkv, bar_v, 2 * H + h * AT_D, tok0);
+    mbar_arrive_expect_tx(&bar_v[0], 16384);
+    tma_load_2d(sV, &tm_qkv, &bar_v[0], 2 * H + h * AT_D, tok0);
   }
 
   const int q = q0 + tid;
@@ -120,28 +120,36 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   float m_used = -INFINITY, l_run = 0.f;
 
   constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
+  // a ragged last key tile (S = 266: 10 keys) only costs its 32-key chunks: S = Q K^T with N = 32 nck, nck chunks of
+  // softmax, 2 nck k16-steps of P V
+  auto nck_of = [&](int j) { return min(AT_N / 32, (S - j * AT_N + 31) >> 5); };
+  auto issue_s = [&](int j) {  // S_j = Q K_j^T (tid 0); its commit also covers every MMA issued before it
+    mbar_wait(bar_k, (uint32_t)(j & 1));
+    tc_fence_after();
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+    const uint32_t idesc_s = make_idesc_bf16(AT_M, nck_of(j) * 32, 0, 0);
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
+    umma_commit(bar_s);
+  };
+  if (tid == 0) {
+    mbar_wait(bar_q, 0);
+    issue_s(0);
+  }
 
+  // Per key tile the threads wait ONCE, for { P V of tile j-1, S of tile j } (S_j is issued right behind P V_{j-1}, so the
+  // tensor pipe runs them back to back); K_{j+1} and V_{j+1} are fetched while the softmax of tile j runs.
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
     const int k0 = j * AT_N;
-    // a ragged last key tile (S = 266: 10 keys) only costs its 32-key chunks: S = Q K^T with N = 32 nck, nck chunks of
-    // softmax, 2 nck k16-steps of P V
-    const int nck = min(AT_N / 32, (S - k0 + 31) >> 5);
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-      const uint32_t idesc_s = make_idesc_bf16(AT_M, nck * 32, 0, 0);
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
-      umma_commit(bar_s);
-    }
+    const int nck = nck_of(j);
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // K tile is free once S = Q K^T has completed
+    if (tid == 0 && j + 1 < n_kv) {  // S_j and P V_{j-1} have completed: the K tile and V buffer (j+1)&1 are free
       mbar_arrive_expect_tx(bar_k, 16384);
       tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + (j + 1) * AT_N);
+      mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], 16384);
+      tma_load_2d(sV + ((j + 1) & 1) * 16384, &tm_qkv, &bar_v[(j + 1) & 1], 2 * H + h * AT_D, tok0 + (j + 1) * AT_N);
     }
     // ---- S row -> registers (log2 domain), masked; row maximum ----
     float x[AT_N];
@@ -212,9 +220,9 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      mbar_wait(bar_v, ph);
+      mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+      const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (j & 1) * 16384);
 #pragma unroll
       for (int k = 0; k < AT_N / 16; ++k) {
         if (k >= 2 * nck) break;
@@ -222,15 +230,12 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         const uint64_t db = desc_mnmajor(va, k, 0);  // single 64-wide chunk: LBO unused
         umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
       }
-      umma_commit(bar_o);
-    }
-    mbar_wait(bar_o, ph);  // P smem, V smem and O are consistent again
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {
-      mbar_arrive_expect_tx(bar_v, 16384);
-      tma_load_2d(sV, &tm_qkv, bar_v, 2 * H + h * AT_D, tok0 + (j + 1) * AT_N);
+      if (j + 1 < n_kv) issue_s(j + 1);  // commits bar_s: P V_j and S_{j+1}
+      else umma_commit(bar_o);
     }
   }
+  mbar_wait(bar_o, 0);  // last P V: O is final
+  tc_fence_after();
 
   {
     const float inv = 1.0f / l_run;
