@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     }
     // ---- S row -> registers (log2 domain), masked; row maximum ----
     float x[AT_N];
-    float mx = -INFINITY;
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max / sum chains instead of a 128-long one
 #pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
       if (c >= nck) break;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           x[c * 32 + i] = __uint_as_float(r[i]) * sc2;
-          mx = fmaxf(mx, x[c * 32 + i]);
+          mx4[i & 3] = fmaxf(mx4[i & 3], x[c * 32 + i]);
         }
       } else {
 #pragma unroll
@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
           t = ((vw >> i) & 1u) ? t : MASKED_LOG2;
           t = ((iw >> i) & 1u) ? t : -INFINITY;
           x[c * 32 + i] = t;
-          mx = fmaxf(mx, t);
+          mx4[i & 3] = fmaxf(mx4[i & 3], t);
         }
       }
     }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     // ---- lazy running max: advance (and correct O in TMEM) only when the row max grew by more than 2^8 ----
     const bool need = mx > m_used + 8.0f;  // always true on the first tile (m_used = -inf)
     if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     }
     if (need) m_used = mx;
     // ---- p = 2^(x - m), P (bf16) into the K-major swizzled A tile ----
-    float rowsum = 0.f;
+    float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < AT_N / 32; ++c) {
       if (c >= nck) break;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float p0 = ex2_approx(x[c * 32 + i] - m_used), p1 = ex2_approx(x[c * 32 + i + 1] - m_used);
-        rowsum += p0 + p1;
+        rs4[(i >> 1) & 3] += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
       uint8_t* atom = sP + (c >> 1) * 16384;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         *reinterpret_cast<uint4*>(atom + sw128_offset(tid, (uint32_t)((c & 1) * 4 + g))) =
             make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
     }
-    l_run += rowsum;
+    l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
