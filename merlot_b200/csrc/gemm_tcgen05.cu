@@ -106,10 +106,8 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   if (bn == -256) { pair = true; bn = 256; }
   if (bn == 0 && (g->flags & MERLOT_GEMM_ATOMIC)) bn = 256;  // wgrad: split-K fills the machine, wide tiles halve smem traffic
   if (bn == 0) {
-    const bool dual = (g->flags & MERLOT_GEMM_GELU) && g->out2 != nullptr;
     double best = -1;
     for (int cand : {256, 192, 128}) {
-      if (dual && cand == 192) continue;  // pre+act staging works in 128-column phases
       long long tiles = (long long)p.m_blocks * ceil_div(g->N, cand);
       long long waves = ceil_div_ll(tiles, sms);
       double useful = (double)g->N / (double)(ceil_div(g->N, cand) * cand);
@@ -118,7 +116,6 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
     }
   }
   MB_REQUIRE(bn == 128 || bn == 192 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128, 192 or 256 (got %d)", bn);
-  MB_REQUIRE(!(bn == 192 && (g->flags & MERLOT_GEMM_GELU) && g->out2), MERLOT_EINVAL, "gemm: block_n 192 cannot be used with a dual (pre+act) output");
   p.n_blocks = ceil_div(g->N, bn);
   if (!pair && pair_auto == 2 && bn == 256 && g->M > 256) pair = true;  // 2 = everywhere (experiments)
   if (!pair && pair_auto == 1 && bn == 256 && g->M > 256 && ((g->flags & MERLOT_GEMM_ATOMIC) || g->K >= 4096)) pair = true;

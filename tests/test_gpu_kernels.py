@@ -76,6 +76,42 @@ def test_gemm_epilogues(ops):
     assert rel(o1.cpu()[kept], (base / 0.9)[kept]) < 6e-3  # inverted dropout scaling (tf.nn.dropout)
 
 
+@pytest.mark.parametrize("bn", [128, 192, 256, -256])  # -256 = CTA-pair kernel
+@pytest.mark.parametrize("M,N", [(300, 264), (130, 1000), (515, 72)])
+def test_gemm_epilogue_instances(ops, bn, M, N):
+    """Every feature-specialised epilogue instance (plain, bias, bias+resid(+generic), bias+gelu dual, gelu', resid) on
+    every tile width, with ragged M and N edges (N % 64 != 0, N % 32 != 0) -- the warp-private staged epilogue clips per
+    16-byte chunk and per row."""
+    if bn == -256 and M <= 256:
+        pytest.skip("the pair kernel needs more than one 256-row tile to be selected")
+    g = torch.Generator().manual_seed(M * 7 + N)
+    K = 200
+    a = (torch.randn(M, K, generator=g) * 0.3).bfloat16()
+    w = (torch.randn(K, N, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(N, generator=g)
+    resid = torch.randn(M, N, generator=g).bfloat16()
+    aux = torch.randn(M, N, generator=g).bfloat16()
+    base = a.float() @ w.float()
+    ad, wd, bd, rd, xd = a.to(DEV), w.to(DEV), bias.to(DEV), resid.to(DEV), aux.to(DEV)
+    kw = dict(b_mn_major=True, block_n=bn)
+    assert rel(ops.gemm(ad, wd, **kw), base) < 6e-3
+    assert rel(ops.gemm(ad, wd, bias=bd, **kw), base + bias) < 6e-3
+    assert rel(ops.gemm(ad, wd, resid=rd, **kw), base + resid.float()) < 6e-3
+    assert rel(ops.gemm(ad, wd, bias=bd, resid=rd, **kw), base + bias + resid.float()) < 6e-3
+    assert rel(ops.gemm(ad, wd, bias=bd, resid=rd, alpha=0.5, **kw), 0.5 * base + bias + resid.float()) < 6e-3  # generic instance
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    act = ops.gemm(ad, wd, bias=bd, gelu=True, out_pre=pre, **kw)
+    assert rel(pre, base + bias) < 6e-3 and rel(act, O.gelu(base + bias)) < 6e-3
+    x = aux.float().requires_grad_(True)
+    O.gelu(x).sum().backward()
+    assert rel(ops.gemm(ad, wd, dgelu_aux=xd, **kw), base * x.grad) < 6e-3
+    assert rel(ops.gemm(ad, wd, dgelu_aux=xd, resid=rd, **kw), base * x.grad + resid.float()) < 6e-3  # gelu' + unprefetched residual
+    dw = torch.zeros(K, N, dtype=torch.float32, device=DEV)  # split-K fp32 accumulation (EPI 2) with ragged N
+    dy = (torch.randn(M, N, generator=g) * 0.1).bfloat16()
+    ops.gemm(ad, dy.to(DEV), a_mn_major=True, b_mn_major=True, out=dw, atomic=True, M=K, N=N, K=M, block_n=bn if bn > 0 else 0)
+    assert rel(dw, a.float().t() @ dy.float()) < 1e-4
+
+
 def test_gemm_shape_errors(ops):
     from merlot_b200._lib import MerlotShapeError
     a = torch.zeros(16, 12, dtype=torch.bfloat16, device=DEV)  # lda = 12 not a multiple of 8
