@@ -12,7 +12,7 @@ constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quadrant, each owning h
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int BIAS_SLOT_BYTES = 1024;                       // 8 epilogue warps x 32 fp32 bias values of the current chunk
 constexpr int SMEM_LIMIT = 232448 - 1024 - 256 - BIAS_SLOT_BYTES;  // 227 KB minus alignment slack, barriers, bias slots
-constexpr int STAGING_BYTES = 32768;             // 2 boxes of [128 rows][128 B], 128B-swizzled (TMA-store epilogue)
+constexpr int STAGING_BYTES = 32768;             // 8 epilogue warps x one 4 KB [32 rows][128 B] 128B-swizzled slot
 
 struct GemmDev {
   int M, N, K;
@@ -143,10 +143,6 @@ __device__ __forceinline__ void epi_store_direct(const GemmDev& p, int row, int 
   }
 }
 
-__device__ __forceinline__ void stage_bf16x8(uint8_t* box, int row_in_tile, int chunk16, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(box + sw128_offset((uint32_t)row_in_tile, (uint32_t)chunk16)) =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
 
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {

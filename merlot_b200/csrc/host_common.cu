@@ -52,7 +52,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                      uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+                      uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(MERLOT_ECUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t dims[2] = {inner, outer};
@@ -60,28 +60,13 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(MERLOT_ECUDA,
                      "cuTensorMapEncodeTiled(2d) failed: CUresult %d (base=%p inner=%llu outer=%llu ld=%llu box=%ux%u)",
                      (int)r, base, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems,
                      box_inner, box_outer);
-  return MERLOT_OK;
-}
-
-int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
-                     uint32_t box_inner, uint32_t box_outer) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return set_error(MERLOT_ECUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 4};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(MERLOT_ECUDA, "cuTensorMapEncodeTiled(f32 2d) failed: CUresult %d", (int)r);
   return MERLOT_OK;
 }
 
