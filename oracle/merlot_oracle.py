@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import copy
 import math
+import re
 from typing import Dict, Optional
 
 import numpy as np
@@ -139,22 +140,157 @@ def transformer(hidden, mask, p: Params, scope: str, num_layers: int, heads: int
 
 
 # ------------------------------------------------------------------------------------------------------------
-# ViT backbone (utils/vision_transformer.py:173-274), patch-embed stem only (resnet_layers == [])
+# Hybrid ResNet-lite stem (utils/vision_transformer.py:8-170) -- SURVEY.md 8(f) next-row 1 / Appendix D.
+# Restated ahead of the CUDA path so that path starts with a checker; merlot_b200 still raises NotImplementedError
+# for resnet_layers != [].
+# ------------------------------------------------------------------------------------------------------------
+def group_norm(x: torch.Tensor, p: Params, scope: str, num_groups: int = 32, eps: float = 1e-4) -> torch.Tensor:
+    """utils/model_utils.py:133-222 as called by batch_norm_relu (vision_transformer.py:22-27): NHWC, 32 groups, eps 1e-4,
+    mean_close_to_zero=True => ONE-PASS moments (sufficient_statistics + normalize_moments, :196-201):
+    mean = sum(x)/n, var = sum(x^2)/n - mean^2 over (h, w, channels-in-group) per (sample, group); gamma/beta per channel."""
+    n, h, w, c = x.shape
+    if c % num_groups != 0:
+        raise ValueError(f"{c} channels is not commensurate with {num_groups} groups")  # :171-177
+    xr = x.reshape(n, h, w, num_groups, c // num_groups)
+    cnt = float(h * w * (c // num_groups))
+    mean = xr.sum((1, 2, 4), keepdim=True) / cnt
+    var = (xr * xr).sum((1, 2, 4), keepdim=True) / cnt - mean * mean
+    y = ((xr - mean) * torch.rsqrt(var + eps)).reshape(n, h, w, c)
+    return y * p[f"{scope}/gamma"] + p[f"{scope}/beta"]
+
+
+def conv2d_fixed_padding(x: torch.Tensor, kernel: torch.Tensor, strides: int = 1, weight_standardization: bool = True) -> torch.Tensor:
+    """vision_transformer.py:30-66.  x NHWC, kernel HWIO, no bias.  strides > 1: explicit pad (k-1)//2 before / the rest after
+    (fixed_padding :8-19) then VALID; strides == 1: SAME.  Weight standardisation (:56-60): per OUTPUT channel, moments over
+    (kh, kw, cin), biased variance, eps 1e-5."""
+    k = kernel.shape[0]
+    if weight_standardization:
+        mean = kernel.mean((0, 1, 2), keepdim=True)
+        var = ((kernel - mean) ** 2).mean((0, 1, 2), keepdim=True)
+        kernel = (kernel - mean) * torch.rsqrt(var + 1e-5)
+    xn = x.permute(0, 3, 1, 2)
+    if strides > 1:
+        beg = (k - 1) // 2
+        xn = F.pad(xn, (beg, k - 1 - beg, beg, k - 1 - beg))
+        y = F.conv2d(xn, kernel.permute(3, 2, 0, 1), stride=strides)
+    else:
+        assert k % 2 == 1
+        y = F.conv2d(xn, kernel.permute(3, 2, 0, 1), padding=k // 2)
+    return y.permute(0, 2, 3, 1)
+
+
+def avg_pool_same(x: torch.Tensor, s: int) -> torch.Tensor:
+    """tf.nn.avg_pool2d(ksize=s, strides=s, padding='SAME') on NHWC: ceil(h/s) outputs, padding at the bottom/right only,
+    padded cells excluded from the average."""
+    return F.avg_pool2d(x.permute(0, 3, 1, 2), s, s, ceil_mode=True, count_include_pad=False).permute(0, 2, 3, 1)
+
+
+class _ScopeNames:
+    """tf.layers / variable_scope default-name uniquification inside ONE variable scope: conv2d, conv2d_1, ... and
+    GroupNorm, GroupNorm_1, ... in creation order."""
+
+    def __init__(self, scope: str):
+        self.scope, self.nconv, self.ngn = scope, 0, 0
+
+    def conv(self) -> str:
+        n = "conv2d" if self.nconv == 0 else f"conv2d_{self.nconv}"
+        self.nconv += 1
+        return f"{self.scope}/{n}/kernel"
+
+    def gn(self, name: Optional[str] = None) -> str:
+        if name is not None:
+            return f"{self.scope}/GroupNorm_{name}"
+        n = "GroupNorm" if self.ngn == 0 else f"GroupNorm_{self.ngn}"
+        self.ngn += 1
+        return f"{self.scope}/{n}"
+
+
+def bottleneck_block(x: torch.Tensor, p: Params, names: _ScopeNames, filters: int, strides: int, use_projection: bool) -> torch.Tensor:
+    """vision_transformer.py:69-96.  Striding is done by average pooling: the shortcut pools BEFORE its 1x1 (:79-83), the main
+    path pools AFTER the 3x3 (:92-93).  Variable creation order: [shortcut conv, GN], 1x1, GN, 3x3, GN, 1x1, GN."""
+    shortcut = x
+    if use_projection:
+        sc_in = avg_pool_same(x, strides) if strides > 1 else x
+        shortcut = group_norm(conv2d_fixed_padding(sc_in, p[names.conv()]), p, names.gn())  # skip_relu=True
+    y = torch.relu(group_norm(conv2d_fixed_padding(x, p[names.conv()]), p, names.gn()))
+    y = torch.relu(group_norm(conv2d_fixed_padding(y, p[names.conv()]), p, names.gn()))
+    if strides > 1:
+        y = avg_pool_same(y, strides)
+    y = group_norm(conv2d_fixed_padding(y, p[names.conv()]), p, names.gn())  # skip_relu=True
+    return torch.relu(y + shortcut)
+
+
+def lite_resnet50(x: torch.Tensor, p: Params, scope: str, layers, width: int = 64) -> torch.Tensor:
+    """vision_transformer.py:118-170: 3-conv stem (3x3 s2, 3x3, 3x3; GN+ReLU each) -> avg-pool 2 -> len(layers) block groups
+    with filters width*2^i, stride 1 for the first group and 2 after."""
+    st = _ScopeNames(f"{scope}/stem")
+    x0 = torch.relu(group_norm(conv2d_fixed_padding(x, p[st.conv()], strides=2), p, st.gn("stem0")))
+    x1 = torch.relu(group_norm(conv2d_fixed_padding(x0, p[st.conv()]), p, st.gn("stem1")))
+    x2 = torch.relu(group_norm(conv2d_fixed_padding(x1, p[st.conv()]), p, st.gn("stem2")))
+    c = avg_pool_same(x2, 2)
+    for i, blocks in enumerate(layers):
+        names = _ScopeNames(f"{scope}/block_group{i + 1}")
+        c = bottleneck_block(c, p, names, width * (2 ** i), 1 if i == 0 else 2, True)  # :109-110
+        for _ in range(1, blocks):
+            c = bottleneck_block(c, p, names, width * (2 ** i), 1, False)
+    return c
+
+
+def resnet_param_shapes(scope: str, layers, width: int = 64, hidden_size: int = 768) -> Dict[str, tuple]:
+    """Variables of the hybrid stem in creation order (names per SURVEY.md Appendix A; unverifiable against a checkpoint here)."""
+    s: Dict[str, tuple] = {}
+
+    def gn(name, c):
+        s[f"{name}/gamma"] = (c,)
+        s[f"{name}/beta"] = (c,)
+
+    st = _ScopeNames(f"{scope}/resnet50lite/stem")
+    for (cin, cout), nm in zip(((3, width // 2), (width // 2, width // 2), (width // 2, width)), ("stem0", "stem1", "stem2")):
+        s[st.conv()] = (3, 3, cin, cout)
+        gn(st.gn(nm), cout)
+    cin = width
+    for i, blocks in enumerate(layers):
+        f = width * (2 ** i)
+        names = _ScopeNames(f"{scope}/resnet50lite/block_group{i + 1}")
+        for b in range(blocks):
+            if b == 0:
+                s[names.conv()] = (1, 1, cin, 4 * f)
+                gn(names.gn(), 4 * f)
+            s[names.conv()] = (1, 1, cin, f)
+            gn(names.gn(), f)
+            s[names.conv()] = (3, 3, f, f)
+            gn(names.gn(), f)
+            s[names.conv()] = (1, 1, f, 4 * f)
+            gn(names.gn(), 4 * f)
+            cin = 4 * f
+    s[f"{scope}/conv_postresnet_proj/kernel"] = (1, 1, cin, hidden_size)
+    s[f"{scope}/conv_postresnet_proj/bias"] = (hidden_size,)
+    return s
+
+
+# ------------------------------------------------------------------------------------------------------------
+# ViT backbone (utils/vision_transformer.py:173-274): patch-embed stem (resnet_layers == []) or the hybrid stem
 # ------------------------------------------------------------------------------------------------------------
 def vision_transformer_backbone(image: torch.Tensor, cfg: dict, p: Params):
     P = cfg["patch_size"]
     H = cfg["hidden_size"]
     num_cls = cfg.get("num_cls_emb", 2)
-    if len(cfg.get("resnet_layers", [])) != 0:
-        raise NotImplementedError("oracle: hybrid ResNet stem (utils/vision_transformer.py:206-223) not restated yet")
+    resnet_layers = cfg.get("resnet_layers", [])
     n, h0, w0, c = image.shape
     assert h0 % P == 0 and w0 % P == 0  # :189-190
     scope = "vision_backbone/vision_transformer"
     x = image - 0.5  # :193
     h1, w1 = h0 // P, w0 // P
-    # conv2d k=P, s=P, VALID == non-overlapping im2col GEMM; kernel HWIO [P,P,3,H] flattened (kh, kw, c)
-    patches = x.reshape(n, h1, P, w1, P, c).permute(0, 1, 3, 2, 4, 5).reshape(n * h1 * w1, P * P * c)
-    x = patches @ p[f"{scope}/conv2d/kernel"].reshape(P * P * c, H) + p[f"{scope}/conv2d/bias"]  # :196-205
+    if len(resnet_layers) == 0:
+        # conv2d k=P, s=P, VALID == non-overlapping im2col GEMM; kernel HWIO [P,P,3,H] flattened (kh, kw, c)
+        patches = x.reshape(n, h1, P, w1, P, c).permute(0, 1, 3, 2, 4, 5).reshape(n * h1 * w1, P * P * c)
+        x = patches @ p[f"{scope}/conv2d/kernel"].reshape(P * P * c, H) + p[f"{scope}/conv2d/bias"]  # :196-205
+    else:
+        assert P == 16  # :208
+        rc = lite_resnet50(x, p, f"{scope}/resnet50lite", resnet_layers, width=64)  # :209-210
+        assert rc.shape[1] == h1 and rc.shape[2] == w1, "the stem reduces by 16 (2 * 2 * 2 * 2)"
+        k = p[f"{scope}/conv_postresnet_proj/kernel"]  # 1x1 SAME with bias, not standardised (:213-223)
+        x = rc.reshape(n * h1 * w1, k.shape[2]) @ k.reshape(k.shape[2], H) + p[f"{scope}/conv_postresnet_proj/bias"]
     x = x.reshape(n, h1 * w1, H)
     x = torch.cat([torch.zeros(n, num_cls, H, dtype=x.dtype), x], 1)  # :231
     x = layer_norm(x + position_embedder2d(p, f"{scope}/pos_embs", h1, w1, num_cls), p,
@@ -498,7 +634,7 @@ def _trunc_normal(shape, std, g):
 
 
 def param_shapes(cfg: dict) -> Dict[str, tuple]:
-    """Every trainable variable the reference creates for the pure-ViT (patch-embed) configuration."""
+    """Every trainable variable the reference creates (patch-embed stem, or the hybrid stem when resnet_layers is set)."""
     H, I, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
     P = cfg["patch_size"]
     s: Dict[str, tuple] = {}
@@ -523,8 +659,11 @@ def param_shapes(cfg: dict) -> Dict[str, tuple]:
         ln(f"{scope}/LayerNorm_ln_final")
 
     vt = "vision_backbone/vision_transformer"
-    s[f"{vt}/conv2d/kernel"] = (P, P, 3, H)
-    s[f"{vt}/conv2d/bias"] = (H,)
+    if len(cfg.get("resnet_layers", [])) == 0:
+        s[f"{vt}/conv2d/kernel"] = (P, P, 3, H)
+        s[f"{vt}/conv2d/bias"] = (H,)
+    else:
+        s.update(resnet_param_shapes(vt, cfg["resnet_layers"], 64, H))
     s[f"{vt}/pos_embs/pos_embs"] = (1, 64, 64, H)
     s[f"{vt}/pos_embs/cls_emb"] = (1, cfg.get("num_cls_emb", 2), H)
     ln(f"{vt}/LayerNorm_ctx_patches_pre_ln")
@@ -570,7 +709,7 @@ def init_params(cfg: dict, seed: int = 0, dtype=torch.float32, perturb: float = 
             t = torch.ones(shape)
         elif leaf in ("beta", "bias", "output_bias"):
             t = torch.zeros(shape)
-        elif name.endswith("conv2d/kernel"):
+        elif re.search(r"/(conv2d(_\d+)?|conv_postresnet_proj)/kernel$", name):  # tf.variance_scaling_initializer() everywhere
             fan_in = shape[0] * shape[1] * shape[2]
             s_ = math.sqrt(1.0 / fan_in) / 0.87962566103423978
             t = _trunc_normal(shape, s_, g)

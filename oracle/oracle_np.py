@@ -68,3 +68,49 @@ def encode_v(v):  # utils/optimization.py:283-288
     err0 = np.abs(e - v)
     err1 = np.abs(e * np.float32(1.00390625) - v)
     return np.where(err0 <= err1, e, -e).astype(np.float32)
+
+
+# ---- hybrid ResNet-lite stem pieces, written independently of merlot_oracle.py --------------------
+def group_norm(x, gamma, beta, num_groups=32, eps=1e-4):  # utils/model_utils.py:133-222, mean_close_to_zero=True
+    n, h, w, c = x.shape
+    g = c // num_groups
+    out = np.empty_like(x)
+    for b in range(n):
+        for k in range(num_groups):
+            blk = x[b, :, :, k * g:(k + 1) * g]
+            m = blk.sum() / blk.size
+            v = (blk * blk).sum() / blk.size - m * m  # one-pass variance (sufficient_statistics / normalize_moments)
+            out[b, :, :, k * g:(k + 1) * g] = (blk - m) / np.sqrt(v + eps)
+    return out * gamma + beta
+
+
+def conv2d_ws(x, kernel, strides=1, ws=True):  # utils/vision_transformer.py:30-66 (NHWC, HWIO), direct loops
+    kh, kw, cin, cout = kernel.shape
+    if ws:
+        flat = kernel.reshape(-1, cout)
+        kernel = ((flat - flat.mean(0)) / np.sqrt(flat.var(0) + 1e-5)).reshape(kernel.shape)
+    n, h, w, _ = x.shape
+    if strides > 1:
+        beg = (kh - 1) // 2
+        end = kh - 1 - beg
+    else:
+        beg = end = kh // 2
+    xp = np.pad(x, ((0, 0), (beg, end), (beg, end), (0, 0)))
+    ho = (h + beg + end - kh) // strides + 1
+    wo = (w + beg + end - kw) // strides + 1
+    out = np.zeros((n, ho, wo, cout), dtype=x.dtype)
+    for i in range(kh):
+        for j in range(kw):
+            patch = xp[:, i:i + (ho - 1) * strides + 1:strides, j:j + (wo - 1) * strides + 1:strides, :]
+            out += patch @ kernel[i, j]
+    return out
+
+
+def avg_pool_same(x, s):  # tf.nn.avg_pool2d SAME, ksize = strides = s: bottom/right padding, padded cells not counted
+    n, h, w, c = x.shape
+    ho, wo = -(-h // s), -(-w // s)
+    out = np.empty((n, ho, wo, c), dtype=x.dtype)
+    for i in range(ho):
+        for j in range(wo):
+            out[:, i, j] = x[:, i * s:min(h, (i + 1) * s), j * s:min(w, (j + 1) * s)].mean((1, 2))
+    return out

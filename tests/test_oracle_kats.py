@@ -192,3 +192,98 @@ def test_adam_oracle_matches_closed_form():  # utils/optimization.py:339-416, fi
         v = 0.02 * (g[k] ** 2 + 1e-30)
         u = m / (v.sqrt() + 1e-6) + (0.1 * p0[k] if "kernel" in k else 0)
         assert torch.allclose(p[k], p0[k] - lr_t * u, rtol=1e-5, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Hybrid ResNet-lite stem: restated in the oracle ahead of the CUDA path
+# ---------------------------------------------------------------------------------------------------------------
+def test_hybrid_stem_stage_shapes_and_parameter_count():  # utils/vision_transformer.py:118-170,206-223
+    vt = "vision_backbone/vision_transformer"
+    shapes = O.resnet_param_shapes(vt, [3, 4, 9], 64, 768)
+    count = lambda pred: sum(int(np.prod(v)) for k, v in shapes.items() if pred(k))
+    expect, cin = (27 * 32 + 9 * 32 * 32 + 9 * 32 * 64) + 2 * (32 + 32 + 64), 64   # three stem convs + their GroupNorms
+    for f, blocks in ((64, 3), (128, 4), (256, 9)):                                # closed form, independent of the name walk
+        expect += cin * 4 * f + 2 * 4 * f                                           # projection shortcut + GN (first block only)
+        for b in range(blocks):
+            expect += (cin if b == 0 else 4 * f) * f + 9 * f * f + f * 4 * f + 2 * (f + f + 4 * f)
+        cin = 4 * f
+    assert count(lambda k: "resnet50lite" in k) == expect == 11_914_080             # 11.91 M
+    assert count(lambda k: "conv_postresnet_proj" in k) == 1024 * 768 + 768  # + 0.79 M
+    # creation-order names inside one variable scope (Appendix A)
+    g1 = [k for k in shapes if "/block_group1/" in k and k.endswith("kernel")]
+    assert [k.split("/")[-2] for k in g1[:5]] == ["conv2d", "conv2d_1", "conv2d_2", "conv2d_3", "conv2d_4"]
+    assert shapes[f"{vt}/resnet50lite/block_group1/conv2d/kernel"] == (1, 1, 64, 256)     # projection shortcut first
+    assert shapes[f"{vt}/resnet50lite/block_group1/conv2d_2/kernel"] == (3, 3, 64, 64)
+    assert shapes[f"{vt}/resnet50lite/block_group3/conv2d/kernel"] == (1, 1, 512, 1024)
+    assert f"{vt}/resnet50lite/stem/GroupNorm_stem2/gamma" in shapes
+    cfg = dict(patch_size=16, hidden_size=768, resnet_layers=[3, 4, 9], num_hidden_layers=1, num_attention_heads=12,
+               intermediate_size=3072, vocab_size=1000, max_position_embeddings=64, spatial_pool_size=2)
+    p = O.init_params(cfg, seed=0)
+    x = torch.rand(1, 192, 352, 3, generator=torch.Generator().manual_seed(0)) - 0.5
+    st = O._ScopeNames(f"{vt}/resnet50lite/stem")
+    x0 = torch.relu(O.group_norm(O.conv2d_fixed_padding(x, p[st.conv()], strides=2), p, st.gn("stem0")))
+    assert tuple(x0.shape) == (1, 96, 176, 32)                                            # Appendix D, stem0
+    rc = O.lite_resnet50(x, p, f"{vt}/resnet50lite", [3, 4, 9])
+    assert tuple(rc.shape) == (1, 12, 22, 1024)                                           # Appendix D, block_group3
+    info = O.vision_transformer_backbone(x + 0.5, cfg, p)
+    assert tuple(info["seq"].shape) == (1, 66, 768) and tuple(info["cls"].shape) == (1, 2, 768)
+
+
+def test_group_norm_and_weight_standardisation_kats():  # utils/model_utils.py:196-205, utils/vision_transformer.py:56-60
+    c = 64
+    p = {"g/gamma": torch.full((c,), 2.0), "g/beta": torch.full((c,), 0.25)}
+    const = torch.ones(2, 3, 5, c) * torch.arange(c).float().div(2, rounding_mode="floor")  # constant inside every group of 2
+    assert torch.allclose(O.group_norm(const, p, "g"), torch.full_like(const, 0.25))       # zero variance -> beta
+    pm = torch.ones(1, 4, 4, c)
+    pm[:, ::2] = -1.0                                                                      # every group: mean 0, E[x^2] = 1
+    assert torch.allclose(O.group_norm(pm, p, "g"), pm * 2.0 / math.sqrt(1.0 + 1e-4) + 0.25, atol=1e-6)
+    with pytest.raises(ValueError):
+        O.group_norm(torch.zeros(1, 2, 2, 48), {"g/gamma": torch.ones(48), "g/beta": torch.zeros(48)}, "g")
+    k = torch.randn(3, 3, 8, 16, generator=torch.Generator().manual_seed(1)) * 3 + 1
+    delta = torch.zeros(1, 5, 5, 8)
+    delta[0, 2, 2, 0] = 1.0  # an impulse reads the standardised kernel back (flipped): y[2-i+1, 2-j+1, :] = k_std[i, j, 0, :]
+    y = O.conv2d_fixed_padding(delta, k)
+    kstd = torch.stack([y[0, 3 - i, 3 - j] for i in range(3) for j in range(3)])           # [9, cout] for cin = 0
+    full = (k - k.mean((0, 1, 2), keepdim=True)) / torch.sqrt(k.var((0, 1, 2), unbiased=False, keepdim=True) + 1e-5)
+    assert torch.allclose(kstd, full[:, :, 0, :].reshape(9, 16), atol=1e-5)
+    assert torch.allclose(full.mean((0, 1, 2)), torch.zeros(16), atol=1e-6)
+
+
+def test_hybrid_stem_two_restatements_agree():  # torch fp64 (merlot_oracle) vs independent numpy fp64 (oracle_np)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 9, 7, 64, generator=g, dtype=torch.float64)
+    gam, bet = torch.randn(64, generator=g, dtype=torch.float64), torch.randn(64, generator=g, dtype=torch.float64)
+    a = O.group_norm(x, {"s/gamma": gam, "s/beta": bet}, "s")
+    assert np.allclose(a.numpy(), N.group_norm(x.numpy(), gam.numpy(), bet.numpy()), rtol=1e-9, atol=1e-9)
+    for k, s_, cin, cout in ((3, 2, 3, 8), (3, 1, 64, 16), (1, 1, 64, 32)):
+        xi = torch.randn(2, 9, 7, cin, generator=g, dtype=torch.float64)
+        w = torch.randn(k, k, cin, cout, generator=g, dtype=torch.float64)
+        assert np.allclose(O.conv2d_fixed_padding(xi, w, strides=s_).numpy(), N.conv2d_ws(xi.numpy(), w.numpy(), s_), rtol=1e-9, atol=1e-9)
+    assert np.allclose(O.avg_pool_same(x, 2).numpy(), N.avg_pool_same(x.numpy(), 2), rtol=1e-12)  # odd sizes: ragged last cell
+    # a whole (tiny) stem end to end, numpy side composed here from the numpy primitives
+    vt = "v"
+    shapes = O.resnet_param_shapes(vt, [1, 1], 64, 32)
+    p = {n_: (torch.randn(sh, generator=g, dtype=torch.float64) * (0.3 if n_.endswith("kernel") else 1.0)) for n_, sh in shapes.items()}
+    img = torch.rand(1, 32, 48, 3, generator=g, dtype=torch.float64) - 0.5
+    ref = O.lite_resnet50(img, p, f"{vt}/resnet50lite", [1, 1]).numpy()
+    q = {k_: v.numpy() for k_, v in p.items()}
+
+    def gn(xn, name):
+        return N.group_norm(xn, q[f"{name}/gamma"], q[f"{name}/beta"])
+
+    st, relu = f"{vt}/resnet50lite/stem", lambda t: np.maximum(t, 0.0)
+    y = relu(gn(N.conv2d_ws(img.numpy(), q[f"{st}/conv2d/kernel"], 2), f"{st}/GroupNorm_stem0"))
+    y = relu(gn(N.conv2d_ws(y, q[f"{st}/conv2d_1/kernel"]), f"{st}/GroupNorm_stem1"))
+    y = relu(gn(N.conv2d_ws(y, q[f"{st}/conv2d_2/kernel"]), f"{st}/GroupNorm_stem2"))
+    y = N.avg_pool_same(y, 2)
+    for gi, stride in ((1, 1), (2, 2)):
+        bg = f"{vt}/resnet50lite/block_group{gi}"
+        sc = gn(N.conv2d_ws(N.avg_pool_same(y, stride) if stride > 1 else y, q[f"{bg}/conv2d/kernel"]), f"{bg}/GroupNorm")
+        z = relu(gn(N.conv2d_ws(y, q[f"{bg}/conv2d_1/kernel"]), f"{bg}/GroupNorm_1"))
+        z = relu(gn(N.conv2d_ws(z, q[f"{bg}/conv2d_2/kernel"]), f"{bg}/GroupNorm_2"))
+        if stride > 1:
+            z = N.avg_pool_same(z, stride)
+        z = gn(N.conv2d_ws(z, q[f"{bg}/conv2d_3/kernel"]), f"{bg}/GroupNorm_3")
+        y = relu(z + sc)
+    assert ref.shape == y.shape == (1, 4, 6, 512)
+    assert np.allclose(ref, y, rtol=1e-7, atol=1e-8)
