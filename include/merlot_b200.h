@@ -75,7 +75,7 @@ typedef struct merlot_gemm {
   uint32_t flags;
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
   int splits;                     /* 0 = auto; >1 requires MERLOT_GEMM_ATOMIC */
-  int block_n;                    /* 0 = auto; else 128, 192 or 256 (tuning / tests) */
+  int block_n;                    /* 0 = auto; else 128, 192 or 256; -256 / -192 force the CTA-pair kernel (tuning / tests) */
 } merlot_gemm_t;
 
 int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream);

@@ -9,12 +9,14 @@
 
 namespace mb {
 
-constexpr int BN2 = 256;                       // pair tile width
-constexpr int A2_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB: this CTA's 128 rows of A
-constexpr int B2_BYTES = (BN2 / 2) * BLOCK_K * 2;        // 16 KB: this CTA's half of B
-constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr int STAGES2 = (SMEM_LIMIT - STAGING_BYTES) / STAGE2_BYTES;  // 6
-constexpr int SMEM2_TOTAL = STAGES2 * STAGE2_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_SLOT_BYTES;
+constexpr int A2_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB: this CTA's 128 rows of A
+template <int BN>  // pair tile width: 256, or 192 (K-major B only) for N = 768-class outputs whose 256-wide tiling wastes a wave
+struct Pair {
+  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;  // 16 / 12 KB: this CTA's half of B
+  static constexpr int STAGE_BYTES = A2_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - STAGING_BYTES) / STAGE_BYTES;  // 6 / 6
+  static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + BIAS_SLOT_BYTES;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -68,11 +70,12 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
                : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EPI, int FL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int FL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const GemmDev p) {
-  constexpr int BN = BN2;
+  static_assert(BN == 256 || (BN == 192 && !B_MN), "an MN-major B half must be a whole number of 64-column TMA boxes");
+  constexpr int STAGES2 = Pair<BN>::STAGES, B2_BYTES = Pair<BN>::B_BYTES, STAGE2_BYTES = Pair<BN>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -256,9 +259,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 }
 
-template <bool A_MN, bool B_MN, int EPI, int FL>
+template <int BN, bool A_MN, bool B_MN, int EPI, int FL>
 static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t stream) {
-  auto kern = gemm2_bf16_kernel<A_MN, B_MN, EPI, FL>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EPI, FL>;
+  constexpr int SMEM2_TOTAL = Pair<BN>::SMEM_TOTAL;
   static bool attr_set = false;
   if (!attr_set) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL));
@@ -271,29 +275,34 @@ static int launch_gemm2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
   return MERLOT_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm2_mn(int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid, cudaStream_t stream) {
-  if (epi == 0) return launch_gemm2_inst<A_MN, B_MN, 0, F_GENERIC>(ta, tb, p, grid, stream);
-  if (epi == 2) return launch_gemm2_inst<A_MN, B_MN, 2, F_ALPHA>(ta, tb, p, grid, stream);
+  if (epi == 0) return launch_gemm2_inst<BN, A_MN, B_MN, 0, F_GENERIC>(ta, tb, p, grid, stream);
+  if (epi == 2) return launch_gemm2_inst<BN, A_MN, B_MN, 2, F_ALPHA>(ta, tb, p, grid, stream);
   switch (fl) {  // same specialised feature sets as the 1-CTA kernel (gemm_kernel.cuh)
-    case 0: return launch_gemm2_inst<A_MN, B_MN, 1, 0>(ta, tb, p, grid, stream);
-    case F_BIAS: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS>(ta, tb, p, grid, stream);
-    case F_BIAS | F_GELU | F_DUAL: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL>(ta, tb, p, grid, stream);
-    case F_DGELU: return launch_gemm2_inst<A_MN, B_MN, 1, F_DGELU>(ta, tb, p, grid, stream);
-    case F_BIAS | F_RESID: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_RESID>(ta, tb, p, grid, stream);
-    case F_BIAS | F_RESID | F_DROP: return launch_gemm2_inst<A_MN, B_MN, 1, F_BIAS | F_RESID | F_DROP>(ta, tb, p, grid, stream);
-    case F_RESID: return launch_gemm2_inst<A_MN, B_MN, 1, F_RESID>(ta, tb, p, grid, stream);
-    default: return launch_gemm2_inst<A_MN, B_MN, 1, F_GENERIC>(ta, tb, p, grid, stream);
+    case 0: return launch_gemm2_inst<BN, A_MN, B_MN, 1, 0>(ta, tb, p, grid, stream);
+    case F_BIAS: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS>(ta, tb, p, grid, stream);
+    case F_BIAS | F_GELU | F_DUAL: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL>(ta, tb, p, grid, stream);
+    case F_DGELU: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_DGELU>(ta, tb, p, grid, stream);
+    case F_BIAS | F_RESID: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID>(ta, tb, p, grid, stream);
+    case F_BIAS | F_RESID | F_DROP: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID | F_DROP>(ta, tb, p, grid, stream);
+    case F_RESID: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_RESID>(ta, tb, p, grid, stream);
+    default: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_GENERIC>(ta, tb, p, grid, stream);
   }
 }
 
-// Called by merlot_gemm_bf16 when the pair kernel is selected.  `p` arrives with n_blocks for BN = 256.
-int launch_gemm_pair(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+// Called by merlot_gemm_bf16 when the pair kernel is selected.  `p` arrives with n_blocks for the tile width `bn`.
+int launch_gemm_pair(int bn, bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
                      cudaStream_t stream) {
-  if (a_mn && b_mn) return launch_gemm2_mn<true, true>(epi, fl, ta, tb, p, grid, stream);
-  if (!a_mn && b_mn) return launch_gemm2_mn<false, true>(epi, fl, ta, tb, p, grid, stream);
-  if (!a_mn && !b_mn) return launch_gemm2_mn<false, false>(epi, fl, ta, tb, p, grid, stream);
-  return launch_gemm2_mn<true, false>(epi, fl, ta, tb, p, grid, stream);
+  if (bn == 192) {
+    if (b_mn) return set_error(MERLOT_EINVAL, "gemm: the 192-wide pair tile needs a K-major B operand");
+    if (a_mn) return launch_gemm2_mn<192, true, false>(epi, fl, ta, tb, p, grid, stream);
+    return launch_gemm2_mn<192, false, false>(epi, fl, ta, tb, p, grid, stream);
+  }
+  if (a_mn && b_mn) return launch_gemm2_mn<256, true, true>(epi, fl, ta, tb, p, grid, stream);
+  if (!a_mn && b_mn) return launch_gemm2_mn<256, false, true>(epi, fl, ta, tb, p, grid, stream);
+  if (!a_mn && !b_mn) return launch_gemm2_mn<256, false, false>(epi, fl, ta, tb, p, grid, stream);
+  return launch_gemm2_mn<256, true, false>(epi, fl, ta, tb, p, grid, stream);
 }
 
 }  // namespace mb

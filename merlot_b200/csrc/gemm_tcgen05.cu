@@ -40,7 +40,7 @@ void gemm_prof_after(void* tok, cudaStream_t stream) {
 }  // namespace mb
 
 namespace mb {
-int launch_gemm_pair(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
+int launch_gemm_pair(int bn, bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
                      cudaStream_t stream);
 template <int BN>
 int launch_gemm_bn(bool a_mn, bool b_mn, int epi, int fl, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int grid,
@@ -104,6 +104,7 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
   static const int pair_auto = [] { const char* e = getenv("MERLOT_GEMM_PAIR"); return e ? atoi(e) : 1; }();
   bool pair = false;
   if (bn == -256) { pair = true; bn = 256; }
+  if (bn == -192) { pair = true; bn = 192; }  // 256 x 192 pair tile (K-major B only)
   if (bn == 0 && (g->flags & MERLOT_GEMM_ATOMIC)) bn = 256;  // wgrad: split-K fills the machine, wide tiles halve smem traffic
   if (bn == 0) {
     double best = -1;
@@ -115,10 +116,14 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
       if (eff > best + 1e-9) { best = eff; bn = cand; }
     }
   }
-  MB_REQUIRE(bn == 128 || bn == 192 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128, 192 or 256 (got %d)", bn);
+  MB_REQUIRE(bn == 128 || bn == 192 || bn == 256, MERLOT_EINVAL, "gemm: block_n must be 0, 128, 192, 256, -192 or -256 (got %d)", bn);
+  MB_REQUIRE(!(pair && bn == 192 && g->b_mn_major), MERLOT_EINVAL, "gemm: block_n -192 (pair tile) needs a K-major B operand");
   p.n_blocks = ceil_div(g->N, bn);
   if (!pair && pair_auto == 2 && bn == 256 && g->M > 256) pair = true;  // 2 = everywhere (experiments)
   if (!pair && pair_auto == 1 && bn == 256 && g->M > 256 && ((g->flags & MERLOT_GEMM_ATOMIC) || g->K >= 4096)) pair = true;
+  // N = 768-class dgrads (192-wide tiles, K-major weights): the pair tile moves 28 KB per k-block and CTA instead of 40 KB
+  static const int pair192_min_k = [] { const char* e = getenv("MERLOT_PAIR192_MINK"); return e ? atoi(e) : 2048; }();
+  if (!pair && pair_auto >= 1 && bn == 192 && !g->b_mn_major && g->M > 256 && g->K >= pair192_min_k && !out_f32) pair = true;
   const int units = pair ? sms / 2 : sms;                                   // schedulable CTAs or CTA pairs
   const int m_tiles = pair ? ceil_div(g->M, 256) : p.m_blocks;
   // ---- split-K (wgrad): fill the machine when the MN tile count is small ----
@@ -164,7 +169,7 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
                  ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0);
   if (epi == 1 && (g->flags & MERLOT_GEMM_GELU) && g->out2)
     MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
-  if (pair) return launch_gemm_pair(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
+  if (pair) return launch_gemm_pair(bn, g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
   if (bn == 256) return launch_gemm_bn<256>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
   if (bn == 192) return launch_gemm_bn<192>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);
   return launch_gemm_bn<128>(g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);

@@ -112,6 +112,29 @@ def test_gemm_epilogue_instances(ops, bn, M, N):
     assert rel(dw, a.float().t() @ dy.float()) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 768, 200), (515, 264, 136), (1000, 72, 2304)])
+def test_gemm_pair192(ops, M, N, K):
+    """256 x 192 CTA-pair tile (block_n = -192): K-major B only (the dgrad orientation), every epilogue family, ragged edges."""
+    from merlot_b200._lib import MerlotError
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 0.3).bfloat16()
+    b = (torch.randn(N, K, generator=g) * 0.1).bfloat16()  # [N, K]: K-major
+    aux = torch.randn(M, N, generator=g).bfloat16()
+    resid = torch.randn(M, N, generator=g).bfloat16()
+    bias = torch.randn(N, generator=g)
+    base = a.float() @ b.float().t()
+    ad, bd = a.to(DEV), b.to(DEV)
+    assert rel(ops.gemm(ad, bd, block_n=-192), base) < 6e-3
+    assert rel(ops.gemm(ad, bd, block_n=-192, out_dtype=torch.float32), base) < 1e-4
+    assert rel(ops.gemm(ad, bd, block_n=-192, bias=bias.to(DEV), resid=resid.to(DEV)), base + bias + resid.float()) < 6e-3
+    x = aux.float().requires_grad_(True)
+    O.gelu(x).sum().backward()
+    assert rel(ops.gemm(ad, bd, block_n=-192, dgelu_aux=aux.to(DEV)), base * x.grad) < 6e-3
+    assert rel(ops.gemm(ad, bd, block_n=192), base) < 6e-3  # same tile width, 1-CTA kernel
+    with pytest.raises((MerlotError, ValueError)):
+        ops.gemm(ad, b.t().contiguous().to(DEV), b_mn_major=True, block_n=-192)  # MN-major B is not tileable in 96-column halves
+
+
 def test_gemm_shape_errors(ops):
     from merlot_b200._lib import MerlotShapeError
     a = torch.zeros(16, 12, dtype=torch.bfloat16, device=DEV)  # lda = 12 not a multiple of 8
