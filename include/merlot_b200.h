@@ -299,6 +299,23 @@ int merlot_small_gemm_f32(const float* A, long long sam, long long sak, const fl
                           int ldc, int M, int N, int K, float alpha, float beta, void* stream);
 int merlot_axpby_f32(const float* x, float* y, long long n, float a, float b, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K13: hybrid ResNet-lite stem, FORWARD pieces (utils/vision_transformer.py:8-170; what merlot.yaml's
+ * `resnet_layers: [3, 4, 9]` selects).  Convolutions themselves are merlot_gemm_bf16 calls on the NHWC activation matrix
+ * (1x1) or on the im2col matrix below (3x3); see csrc/stem.cu.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* weight standardisation (:56-60): w fp32 [rows = kh*kw*cin, cout] -> bf16 [rows_pad, cout] (rows past `rows` zero) */
+int merlot_ws_weights(const float* w, int rows, int rows_pad, int cout, void* out_bf16, void* stream);
+/* 3x3 taps of an NHWC bf16 tensor with one ring of zero padding, stride 1 (SAME) or 2 (fixed_padding :8-19 + VALID);
+ * out [N*ho*wo, ld], columns (ky, kx, c), columns >= 9*C zero; sub_half: subtract 0.5 from in-range pixels (:193) */
+int merlot_im2col3x3(const void* x_bf16, int N, int h, int w, int C, int stride, int sub_half, void* out_bf16, int ld, void* stream);
+/* batch_norm_relu (:22-27): GroupNorm(groups, eps) with one-pass moments (utils/model_utils.py:196-201), optional ReLU,
+ * optional relu(y + shortcut) (:96).  stats: f32 scratch [N, groups, 2]. */
+int merlot_group_norm_fwd(const void* x_bf16, const float* gamma, const float* beta, const void* shortcut_bf16, void* y_bf16,
+                          float* stats, int N, int HW, int C, int groups, float eps, int relu, void* stream);
+/* tf.nn.avg_pool2d(ksize 2, strides 2, 'SAME') on NHWC bf16 (:81,93,159) */
+int merlot_avgpool2_same(const void* x_bf16, int N, int h, int w, int C, void* y_bf16, void* stream);
+
 /* bench.py roofline support: time every K1 launch with CUDA events on its own stream between begin/end.
  * end() synchronises the device and returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count. */
 void merlot_gemm_profile_begin(void);

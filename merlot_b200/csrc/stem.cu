@@ -1,0 +1,243 @@
+// K13: forward pieces of the hybrid ResNet-lite stem (utils/vision_transformer.py:8-170; SURVEY.md 8(f) next-row 1,
+// Appendix D).  Every convolution is a K1 GEMM: 1x1 convs read the NHWC activation matrix [N*h*w, C] as it is, 3x3
+// convs go through an im2col matrix whose columns are ordered (ky, kx, c) like the flattened HWIO kernel.  This file
+// holds what sits between the GEMMs:
+//   ws_kernel         weight standardisation (vision_transformer.py:56-60): per OUTPUT channel over (kh, kw, cin), biased
+//                     variance, eps 1e-5, fp32 -> bf16 GEMM operand [K_pad, cout]
+//   im2col3x3_*       3x3 taps with one ring of zero padding, stride 1 (SAME) or 2 (fixed_padding :8-19 + VALID); the
+//                     stride-2 first conv reads the image and subtracts 0.5 (:193) BEFORE the padding zeros
+//   gn_stats / apply  batch_norm_relu (:22-27) = GroupNorm(32 groups, eps 1e-4) with the ONE-PASS moments of
+//                     utils/model_utils.py:196-201 (mean = sum/n, var = sum(x^2)/n - mean^2), gamma/beta per channel, bf16
+//                     out, optional ReLU, optional `relu(out + shortcut)` (bottleneck_block :96)
+//   avgpool2          tf.nn.avg_pool2d(ksize 2, strides 2, SAME) (:81,93,159): bottom/right padding not counted
+// Forward only: training through the stem (its backward) is not provided yet and the host raises before getting here.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+__global__ void __launch_bounds__(256) ws_kernel(const float* __restrict__ w, int rows, int rows_pad, int cout, bf16* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output channel: coalesced across the row
+  if (c >= cout) return;
+  float mean = 0.f;
+  for (int r = 0; r < rows; ++r) mean += w[(size_t)r * cout + c];
+  mean /= (float)rows;
+  float var = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float d = w[(size_t)r * cout + c] - mean;
+    var += d * d;
+  }
+  var /= (float)rows;
+  const float s = rsqrtf(var + 1e-5f);
+  for (int r = 0; r < rows; ++r) out[(size_t)r * cout + c] = __float2bfloat16_rn((w[(size_t)r * cout + c] - mean) * s);
+  for (int r = rows; r < rows_pad; ++r) out[(size_t)r * cout + c] = __float2bfloat16_rn(0.f);
+}
+
+// C % 8 == 0: one thread per (output pixel, tap, 8 channels)
+__global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const bf16* __restrict__ x, int N, int h, int w, int C, int stride, int ho,
+                                                            int wo, bf16* __restrict__ out, int ld, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const int tap = (int)((idx / c8n) % 9);
+  const long long row = idx / (9LL * c8n);
+  const int ox = (int)(row % wo), oy = (int)((row / wo) % ho), n = (int)(row / ((long long)wo * ho));
+  const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+    v = *reinterpret_cast<const uint4*>(x + (((size_t)n * h + iy) * w + ix) * C + c8 * 8);
+  *reinterpret_cast<uint4*>(out + (size_t)row * ld + tap * C + c8 * 8) = v;
+}
+
+// any C (the 3-channel image): one thread per (output pixel, column); columns [9C, ld) are zero padding for the GEMM's K
+__global__ void __launch_bounds__(256) im2col3x3_scalar_kernel(const bf16* __restrict__ x, int N, int h, int w, int C, int stride, int ho,
+                                                               int wo, bf16* __restrict__ out, int ld, int sub_half, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int col = (int)(idx % ld);
+  const long long row = idx / ld;
+  float v = 0.f;
+  if (col < 9 * C) {
+    const int tap = col / C, c = col % C;
+    const int ox = (int)(row % wo), oy = (int)((row / wo) % ho), n = (int)(row / ((long long)wo * ho));
+    const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      v = __bfloat162float(x[(((size_t)n * h + iy) * w + ix) * C + c]);
+      if (sub_half) v -= 0.5f;  // img_norm = image - 0.5 (vision_transformer.py:193); the padding ring stays 0
+    }
+  }
+  out[(size_t)row * ld + col] = __float2bfloat16_rn(v);
+}
+
+// per (sample, group): sum and sum of squares over (h*w, channels of the group).  grid (slabs, N); stats must be zero on entry.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, int HW, int C, int groups, int rows_per_block,
+                                                       float* __restrict__ stats) {
+  extern __shared__ float acc[];  // [groups][2]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int c8n = C >> 3;
+  const int lanes = blockDim.x / c8n > 0 ? blockDim.x / c8n : 1;  // rows processed in parallel
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (rl < lanes && c8 < c8n) {
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + ((size_t)n * HW + r) * C + c8 * 8);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(wv[i]);
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      }
+    }
+    const int cg = C / groups;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c8 * 8 + i) / cg;
+      atomicAdd(&acc[2 * g], s[i]);
+      atomicAdd(&acc[2 * g + 1], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)n * 2 * groups + i], acc[i]);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const bf16* __restrict__ shortcut, bf16* __restrict__ y, int HW, int C, int groups,
+                                                       float eps, int relu, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long row = idx / c8n;
+  const int n = (int)(row / HW);
+  const int cg = C / groups;
+  const float inv_cnt = 1.0f / ((float)HW * (float)cg);
+  const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)row * C + c8 * 8);
+  const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(wv[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  float sc[8];
+  if (shortcut != nullptr) {
+    const uint4 su = *reinterpret_cast<const uint4*>(shortcut + (size_t)row * C + c8 * 8);
+    const uint32_t sw[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(sw[i]); sc[2 * i] = f.x; sc[2 * i + 1] = f.y; }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c8 * 8 + i;
+    const int g = c / cg;
+    const float mean = stats[((size_t)n * groups + g) * 2] * inv_cnt;
+    const float var = stats[((size_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean;  // one-pass moments (model_utils.py:196-201)
+    float o = (v[i] - mean) * rsqrtf(var + eps) * gamma[c] + beta[c];
+    if (shortcut != nullptr) o = __bfloat162float(__float2bfloat16_rn(o)) + sc[i];  // bf16 tensor + bf16 tensor (:96)
+    if (relu) o = fmaxf(o, 0.f);
+    v[i] = o;
+  }
+  *reinterpret_cast<uint4*>(y + (size_t)row * C + c8 * 8) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__global__ void __launch_bounds__(256) avgpool2_kernel(const bf16* __restrict__ x, int N, int h, int w, int C, int ho, int wo,
+                                                       bf16* __restrict__ y, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long row = idx / c8n;
+  const int ox = (int)(row % wo), oy = (int)((row / wo) % ho), n = (int)(row / ((long long)wo * ho));
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  int cnt = 0;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int iy = oy * 2 + dy, ix = ox * 2 + dx;
+      if (iy < h && ix < w) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x + (((size_t)n * h + iy) * w + ix) * C + c8 * 8);
+        const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(wv[i]); a[2 * i] += f.x; a[2 * i + 1] += f.y; }
+        ++cnt;
+      }
+    }
+  const float inv = 1.0f / (float)cnt;
+  *reinterpret_cast<uint4*>(y + (size_t)row * C + c8 * 8) =
+      make_uint4(pack_bf16x2(a[0] * inv, a[1] * inv), pack_bf16x2(a[2] * inv, a[3] * inv), pack_bf16x2(a[4] * inv, a[5] * inv),
+                 pack_bf16x2(a[6] * inv, a[7] * inv));
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+#define GRID1D(n) (unsigned)ceil_div_ll((n), 256), 256, 0, st
+
+extern "C" int merlot_ws_weights(const float* w, int rows, int rows_pad, int cout, void* out_bf16, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(w && out_bf16, MERLOT_EINVAL, "ws_weights: null pointer");
+  MB_REQUIRE(rows > 0 && rows_pad >= rows && cout > 0, MERLOT_ESHAPE, "ws_weights: bad shape rows=%d rows_pad=%d cout=%d", rows, rows_pad, cout);
+  ws_kernel<<<GRID1D((long long)cout)>>>(w, rows, rows_pad, cout, (bf16*)out_bf16);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_im2col3x3(const void* x_bf16, int N, int h, int w, int C, int stride, int sub_half, void* out_bf16, int ld,
+                                void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(x_bf16 && out_bf16, MERLOT_EINVAL, "im2col3x3: null pointer");
+  MB_REQUIRE(N > 0 && h > 0 && w > 0 && C > 0 && (stride == 1 || stride == 2), MERLOT_ESHAPE, "im2col3x3: bad shape / stride %d", stride);
+  MB_REQUIRE(ld >= 9 * C && ld % 8 == 0, MERLOT_ESHAPE, "im2col3x3: ld=%d must be >= 9*C and a multiple of 8", ld);
+  const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+  const long long rows = (long long)N * ho * wo;
+  if (C % 8 == 0 && ld == 9 * C && !sub_half) {
+    const long long total = rows * 9 * (C / 8);
+    im2col3x3_vec_kernel<<<GRID1D(total)>>>((const bf16*)x_bf16, N, h, w, C, stride, ho, wo, (bf16*)out_bf16, ld, total);
+  } else {
+    const long long total = rows * ld;
+    im2col3x3_scalar_kernel<<<GRID1D(total)>>>((const bf16*)x_bf16, N, h, w, C, stride, ho, wo, (bf16*)out_bf16, ld, sub_half, total);
+  }
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_group_norm_fwd(const void* x_bf16, const float* gamma, const float* beta, const void* shortcut_bf16, void* y_bf16,
+                                     float* stats, int N, int HW, int C, int groups, float eps, int relu, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(x_bf16 && gamma && beta && y_bf16 && stats, MERLOT_EINVAL, "group_norm_fwd: null pointer");
+  MB_REQUIRE(groups > 0 && C % groups == 0, MERLOT_ESHAPE, "group_norm_fwd: %d channels is not commensurate with %d groups", C, groups);
+  MB_REQUIRE(C % 8 == 0 && C / 8 <= 256 && groups <= 1024, MERLOT_ESHAPE, "group_norm_fwd: C must be a multiple of 8 and <= 2048 (got %d)", C);
+  if (N == 0 || HW == 0) return MERLOT_OK;
+  MB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)groups * N, st));
+  const int lanes = 256 / (C / 8);
+  int rows_per_block = lanes * 32;  // every thread reduces ~32 rows before touching shared memory
+  if (rows_per_block > HW) rows_per_block = HW;
+  dim3 grid((unsigned)ceil_div(HW, rows_per_block), (unsigned)N);
+  gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(float), st>>>((const bf16*)x_bf16, HW, C, groups, rows_per_block, stats);
+  MB_CHECK_LAUNCH();
+  const long long total = (long long)N * HW * (C / 8);
+  gn_apply_kernel<<<GRID1D(total)>>>((const bf16*)x_bf16, stats, gamma, beta, (const bf16*)shortcut_bf16, (bf16*)y_bf16, HW, C, groups,
+                                     eps, relu, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_avgpool2_same(const void* x_bf16, int N, int h, int w, int C, void* y_bf16, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(x_bf16 && y_bf16, MERLOT_EINVAL, "avgpool2_same: null pointer");
+  MB_REQUIRE(C % 8 == 0 && N > 0 && h > 0 && w > 0, MERLOT_ESHAPE, "avgpool2_same: C must be a multiple of 8 (got %d)", C);
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  const long long total = (long long)N * ho * wo * (C / 8);
+  avgpool2_kernel<<<GRID1D(total)>>>((const bf16*)x_bf16, N, h, w, C, ho, wo, (bf16*)y_bf16, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}

@@ -148,6 +148,8 @@ class MerlotModel(object):
             raise NotImplementedError("disable_pairwise_lang_attn (model/modeling.py:160-168) not provided yet")
         if not cfg.get("share_params", True):
             raise NotImplementedError("share_params: False (separate langonly_encoder, model/modeling.py:361) not provided yet")
+        # hybrid ResNet-lite stem (utils/vision_transformer.py:206-223) instead of the 16x16 patch embedding: forward provided
+        self._resnet_layers = list(cfg.get("resnet_layers", []) or [])
 
         input_ids_shape = get_shape_list_rank(input_ids, [2, 3], "input_ids")
         if len(input_ids_shape) == 2:  # :72-77
@@ -254,10 +256,19 @@ class MerlotModel(object):
         # ---- ViT (utils/vision_transformer.py:173-274) ----
         img = image if image.dtype == torch.bfloat16 else image.to(torch.bfloat16)
         img = img.contiguous()
-        A = bf.get("vit.A", (N * np_, Pp * Pp * 3), torch.bfloat16)
-        ops.patch_im2col(img, A, Pp)
         patch = bf.get("vit.patch", (N * np_, H), torch.float32)
-        ops.gemm(A, st.W(f"{vt}/conv2d/kernel"), b_mn_major=True, bias=st.P(f"{vt}/conv2d/bias"), out=patch)
+        if not self._resnet_layers:
+            A = bf.get("vit.A", (N * np_, Pp * Pp * 3), torch.bfloat16)
+            ops.patch_im2col(img, A, Pp)
+            ops.gemm(A, st.W(f"{vt}/conv2d/kernel"), b_mn_major=True, bias=st.P(f"{vt}/conv2d/bias"), out=patch)
+        else:  # hybrid stem (:206-223): lite_resnet50 -> 1x1 conv_postresnet_proj with bias (not standardised)
+            if Pp != 16:
+                raise ValueError("the hybrid ResNet stem needs patch_size 16 (utils/vision_transformer.py:208)")
+            rc, hs, ws_ = self._hybrid_stem(img, N, h0, w0)
+            if (hs, ws_) != (h1, w1):
+                raise ValueError(f"stem output {hs}x{ws_} != patch grid {h1}x{w1}")
+            ops.gemm(rc, st.W(f"{vt}/conv_postresnet_proj/kernel"), b_mn_major=True, bias=st.P(f"{vt}/conv_postresnet_proj/bias"),
+                     out=patch)
         xsum_v = bf.get("vit.xsum", (Mv, H), torch.float32)
         ops.vit_assemble_fwd(patch, st.P(f"{vt}/pos_embs/pos_embs"), st.P(f"{vt}/pos_embs/cls_emb"), xsum_v, N, h1, w1, ncls, H)
         h0_v = bf.get("vit.h0", (Mv, H), torch.bfloat16)
@@ -325,6 +336,92 @@ class MerlotModel(object):
         self._hidden_f32 = {}
         self.encoder_pieces = [{"name": "viz", "start": 0, "end": Pz}, {"name": "lang", "start": Pz, "end": Sj}]
         self._heads = {}
+
+    def _hybrid_stem(self, img, N, h0, w0):
+        """lite_resnet50 (utils/vision_transformer.py:118-170), FORWARD only: NHWC bf16 activations as [N*h*w, C] matrices, every
+        conv a K1 GEMM on weight-standardised bf16 kernels (1x1: the activation matrix itself; 3x3: an im2col matrix), GroupNorm32
+        (+ReLU / +shortcut) and the avg-pool striding as K13 kernels (csrc/stem.cu).  Variables are consumed in the reference's
+        creation order (params.stem_variables).  Returns ([N*h*w, 4*f_last] bf16, h, w)."""
+        st, bf = self.store, self._bufs
+        vt = "vision_backbone/vision_transformer"
+        stats = bf.get("stem.gn_stats", (N * 64,), torch.float32)
+
+        class _Names:  # tf default-name uniquification inside one variable scope
+            def __init__(self, scope):
+                self.scope, self.nc, self.ng = scope, 0, 0
+
+            def conv(self):
+                n = f"{self.scope}/conv2d{'' if self.nc == 0 else '_%d' % self.nc}/kernel"
+                self.nc += 1
+                return n
+
+            def gn(self, name=None):
+                if name is not None:
+                    return f"{self.scope}/GroupNorm_{name}"
+                n = f"{self.scope}/GroupNorm{'' if self.ng == 0 else '_%d' % self.ng}"
+                self.ng += 1
+                return n
+
+        def T(tag, rows, cols):
+            return bf.get(f"stem.{tag}", (rows, cols), torch.bfloat16)
+
+        def conv(x, h, w, cin, kname, k, tag, stride=1, sub_half=False):
+            wk = st.P(kname)  # fp32 [k*k*cin, cout]
+            rows, cout = wk.shape
+            assert rows == k * k * cin, (kname, rows, k, cin)
+            kp = (rows + 7) // 8 * 8
+            wstd = ops.ws_weights(wk, kp)  # :56-60 (fp32 moments, bf16 operand)
+            if k == 1:
+                a, ho, wo = x, h, w
+            else:
+                ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+                a = T("col", N * ho * wo, kp)
+                ops.im2col3x3(x, N, h, w, cin, stride, a, sub_half=sub_half)
+            y = T(tag, N * ho * wo, cout)
+            ops.gemm(a, wstd, b_mn_major=True, out=y)
+            return y, ho, wo, cout
+
+        def gn(x, hw, c, scope_name, tag, relu=True, shortcut=None):
+            y = T(tag, N * hw, c)
+            ops.group_norm_fwd(x, st.P(f"{scope_name}/gamma"), st.P(f"{scope_name}/beta"), y, stats, N, hw, c, 32, 1e-4, relu, shortcut)
+            return y
+
+        def pool(x, h, w, c, tag):
+            ho, wo = (h + 1) // 2, (w + 1) // 2
+            y = T(tag, N * ho * wo, c)
+            ops.avgpool2_same(x, N, h, w, c, y)
+            return y, ho, wo
+
+        nm = _Names(f"{vt}/resnet50lite/stem")
+        x, h, w, c = conv(img, h0, w0, 3, nm.conv(), 3, "s0", stride=2, sub_half=True)  # :138-144 on image - 0.5 (:193)
+        x = gn(x, h * w, c, nm.gn("stem0"), "s0g")
+        x, h, w, c = conv(x, h, w, c, nm.conv(), 3, "s1")
+        x = gn(x, h * w, c, nm.gn("stem1"), "s1g")
+        x, h, w, c = conv(x, h, w, c, nm.conv(), 3, "s2")
+        x = gn(x, h * w, c, nm.gn("stem2"), "s2g")
+        x, h, w = pool(x, h, w, c, "s2p")  # :159
+        for i, blocks in enumerate(self._resnet_layers):
+            nm = _Names(f"{vt}/resnet50lite/block_group{i + 1}")
+            f = 64 * (2 ** i)
+            for b in range(blocks):  # bottleneck_block (:69-96); only the first block of a group projects and strides (:109-113)
+                stride = 2 if (b == 0 and i > 0) else 1
+                shortcut = x
+                if b == 0:
+                    sx, sh, sw = pool(x, h, w, c, f"g{i}sp") if stride > 1 else (x, h, w)
+                    sy, _, _, c4 = conv(sx, sh, sw, c, nm.conv(), 1, f"g{i}sc")
+                    shortcut = gn(sy, sh * sw, c4, nm.gn(), f"g{i}scg", relu=False)
+                y, _, _, c1 = conv(x, h, w, c, nm.conv(), 1, f"g{i}a")
+                y = gn(y, h * w, c1, nm.gn(), f"g{i}ag")
+                y, _, _, c2 = conv(y, h, w, c1, nm.conv(), 3, f"g{i}b")
+                y = gn(y, h * w, c2, nm.gn(), f"g{i}bg")
+                hh, ww = h, w
+                if stride > 1:
+                    y, hh, ww = pool(y, h, w, c2, f"g{i}bp")
+                y, _, _, c3 = conv(y, hh, ww, c2, nm.conv(), 1, f"g{i}c")
+                x = gn(y, hh * ww, c3, nm.gn(), f"g{i}out{b % 2}", relu=True, shortcut=shortcut)  # relu(GN(y) + shortcut) (:95-96)
+                h, w, c = hh, ww, c3
+                assert c3 == 4 * f
+        return x, h, w
 
     def _side_stream(self):
         """Stream for the language-only stack (set MERLOT_NO_SIDE_STREAM=1 to serialise everything on one stream)."""
@@ -772,6 +869,10 @@ class MerlotModel(object):
         -> ViT."""
         if not self._save:
             raise RuntimeError("MerlotModel was built without save_for_backward (is_training=False)")
+        if self._resnet_layers:
+            raise NotImplementedError(
+                "training through the hybrid ResNet-lite stem (resnet_layers={}) is not provided yet: its forward runs (inference / "
+                "zero-shot configs), its backward does not; use config.patch_embed_variant() to train".format(self._resnet_layers))
         cfg, st, bf, D = self.config, self.store, self._bufs, self._dims
         H, B, Lj, N = self.hidden_size, self.B, self.L, D["N"]
         Sj, Pz, vcl, Sv, Mv, np_, ncls = D["Sj"], D["Pz"], D["vcl"], D["Sv"], D["Mv"], D["np"], D["ncls"]

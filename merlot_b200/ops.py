@@ -275,6 +275,29 @@ def patch_im2col(image, a, P):
     L.check(L.lib().merlot_patch_im2col(C.c_void_p(image.data_ptr()), C.c_void_p(a.data_ptr()), N, H0, W0, P, _stream()))
 
 
+def ws_weights(w2d: torch.Tensor, rows_pad: int) -> torch.Tensor:
+    """K13: weight-standardised bf16 GEMM operand [rows_pad, cout] of a conv kernel stored as fp32 [kh*kw*cin, cout]."""
+    rows, cout = w2d.shape
+    out = torch.empty((rows_pad, cout), dtype=torch.bfloat16, device=w2d.device)
+    L.check(L.lib().merlot_ws_weights(C.c_void_p(w2d.data_ptr()), rows, rows_pad, cout, C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
+def im2col3x3(x: torch.Tensor, N, h, w, Cin, stride, out: torch.Tensor, sub_half=False):
+    L.check(L.lib().merlot_im2col3x3(C.c_void_p(x.data_ptr()), N, h, w, Cin, stride, int(sub_half), C.c_void_p(out.data_ptr()),
+                                     out.stride(0), _stream()))
+
+
+def group_norm_fwd(x, gamma, beta, y, stats, N, HW, Cc, groups=32, eps=1e-4, relu=True, shortcut=None):
+    L.check(L.lib().merlot_group_norm_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()),
+                                          C.c_void_p(_ptr(shortcut)), C.c_void_p(y.data_ptr()), C.c_void_p(stats.data_ptr()), N, HW, Cc,
+                                          groups, C.c_float(eps), int(relu), _stream()))
+
+
+def avgpool2_same(x, N, h, w, Cc, y):
+    L.check(L.lib().merlot_avgpool2_same(C.c_void_p(x.data_ptr()), N, h, w, Cc, C.c_void_p(y.data_ptr()), _stream()))
+
+
 def vit_assemble_fwd(patch, pos_table, cls_emb, xsum, N, h1, w1, ncls, H):
     L.check(L.lib().merlot_vit_assemble_fwd(C.c_void_p(patch.data_ptr()), C.c_void_p(pos_table.data_ptr()),
                                             C.c_void_p(cls_emb.data_ptr()), C.c_void_p(xsum.data_ptr()), N, h1, w1, ncls, 64, H,

@@ -64,8 +64,13 @@ def _entries(cfg: dict) -> List[Entry]:
         ln(f"{scope}/LayerNorm_ln_final")
 
     vt = "vision_backbone/vision_transformer"
-    add(f"{vt}/conv2d/kernel", (P * P * 3, H))
-    add(f"{vt}/conv2d/bias", (H,))
+    resnet_layers = list(cfg.get("resnet_layers", []) or [])
+    if not resnet_layers:
+        add(f"{vt}/conv2d/kernel", (P * P * 3, H))
+        add(f"{vt}/conv2d/bias", (H,))
+    else:
+        for nm, shp in stem_variables(vt, resnet_layers, 64, H):  # conv kernels stored [kh*kw*cin, cout] (flattened HWIO)
+            add(nm, shp if len(shp) == 1 else (shp[0] * shp[1] * shp[2], shp[3]))
     add(f"{vt}/pos_embs/pos_embs", (64 * 64, H))
     add(f"{vt}/pos_embs/cls_emb", (cfg.get("num_cls_emb", 2), H))
     ln(f"{vt}/LayerNorm_ctx_patches_pre_ln")
@@ -99,6 +104,54 @@ def _entries(cfg: dict) -> List[Entry]:
     return out
 
 
+def stem_variables(scope: str, layers, width: int, hidden: int):
+    """Variables of the hybrid ResNet-lite stem in the reference's creation order (utils/vision_transformer.py:69-170,213-223;
+    names per SURVEY.md Appendix A: conv2d, conv2d_1, ... / GroupNorm, GroupNorm_1, ... uniquified inside each variable scope).
+    Yields (name, TF shape) with conv kernels HWIO."""
+    out = []
+
+    class _Scope:
+        def __init__(self, s):
+            self.s, self.nc, self.ng = s, 0, 0
+
+        def conv(self, kh, cin, cout):
+            out.append((f"{self.s}/conv2d{'' if self.nc == 0 else '_%d' % self.nc}/kernel", (kh, kh, cin, cout)))
+            self.nc += 1
+
+        def gn(self, c, name=None):
+            base = f"{self.s}/GroupNorm_{name}" if name is not None else f"{self.s}/GroupNorm{'' if self.ng == 0 else '_%d' % self.ng}"
+            if name is None:
+                self.ng += 1
+            out.append((f"{base}/gamma", (c,)))
+            out.append((f"{base}/beta", (c,)))
+
+    st = _Scope(f"{scope}/resnet50lite/stem")
+    for i, (cin, cout) in enumerate(((3, width // 2), (width // 2, width // 2), (width // 2, width))):
+        st.conv(3, cin, cout)
+        st.gn(cout, f"stem{i}")
+    cin = width
+    for i, blocks in enumerate(layers):
+        f = width * (2 ** i)
+        bg = _Scope(f"{scope}/resnet50lite/block_group{i + 1}")
+        for b in range(blocks):
+            if b == 0:  # projection shortcut is created first (:77-85)
+                bg.conv(1, cin, 4 * f)
+                bg.gn(4 * f)
+            bg.conv(1, cin, f)
+            bg.gn(f)
+            bg.conv(3, f, f)
+            bg.gn(f)
+            bg.conv(1, f, 4 * f)
+            bg.gn(4 * f)
+            cin = 4 * f
+    out.append((f"{scope}/conv_postresnet_proj/kernel", (1, 1, cin, hidden)))
+    out.append((f"{scope}/conv_postresnet_proj/bias", (hidden,)))
+    return out
+
+
+_CONV_KERNEL = re.compile(r"/(conv2d(_\d+)?|conv_postresnet_proj)/kernel$")
+
+
 def hyper_for(tf_name: str, optimizer_cfg: dict) -> Tuple[float, float, float, float, float]:
     """(learning_rate, weight_decay_rate, beta_1, beta_2, epsilon) after the regex overrides of
     utils/optimization.py:125-147 (re.search on the variable name; later rules update earlier ones)."""
@@ -127,11 +180,8 @@ class ParamStore:
     """Flat arenas + named views.  `optimizer_cfg` fixes the hyper-parameter grouping (needed only for training)."""
 
     def __init__(self, model_cfg: dict, device="cuda", optimizer_cfg: Optional[dict] = None, with_optimizer_state=True):
-        if len(model_cfg.get("resnet_layers", []) or []) != 0:
-            raise NotImplementedError(
-                "resnet_layers={} selects the hybrid ResNet-lite stem (utils/vision_transformer.py:206-223), which this "
-                "build does not provide yet; use config.patch_embed_variant() for the 16x16 patch-embed ViT".format(
-                    model_cfg.get("resnet_layers")))
+        # resnet_layers != [] selects the hybrid ResNet-lite stem (utils/vision_transformer.py:206-223): its FORWARD is provided
+        # (inference / zero-shot configs); MerlotModel raises NotImplementedError when asked to train through it.
         self.cfg = model_cfg
         self.device = torch.device(device)
         ents = _entries(model_cfg)
@@ -230,9 +280,13 @@ class ParamStore:
                     out[nm] = part.contiguous()
             elif "temporal/logits" in e.name:
                 out[e.tf_names[0]] = t[..., :4].contiguous()
-            elif e.name.endswith("conv2d/kernel"):
+            elif e.name.endswith("vision_transformer/conv2d/kernel"):
                 Pp = self.cfg["patch_size"]
                 out[e.tf_names[0]] = t.reshape(Pp, Pp, 3, -1)
+            elif _CONV_KERNEL.search(e.name):  # hybrid stem: [kh*kw*cin, cout] -> HWIO
+                kh = {n_: s_ for n_, s_ in stem_variables("vision_backbone/vision_transformer", self.cfg["resnet_layers"], 64,
+                                                          self.cfg["hidden_size"])}[e.name][0]
+                out[e.tf_names[0]] = t.reshape(kh, kh, t.shape[0] // (kh * kh), -1)
             elif e.name.endswith("/pos_embs"):
                 out[e.tf_names[0]] = t.reshape(1, 64, 64, -1)
             elif e.name.endswith("/cls_emb"):
@@ -254,7 +308,7 @@ class ParamStore:
                     t = torch.zeros(e.shape)
                 else:
                     s_ = std
-                    if e.name.endswith("conv2d/kernel"):
+                    if _CONV_KERNEL.search(e.name):  # tf.variance_scaling_initializer(): fan_in = kh*kw*cin = rows of the 2-D view
                         s_ = math.sqrt(1.0 / e.shape[0]) / 0.87962566103423978
                     t = torch.empty(e.shape)
                     torch.nn.init.trunc_normal_(t, 0.0, s_, -2 * s_, 2 * s_, generator=g)

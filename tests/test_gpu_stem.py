@@ -1,0 +1,111 @@
+"""GPU parity of the hybrid ResNet-lite stem's FORWARD: the K13 kernels one by one against the
+oracle's primitives, then lite_resnet50 and the whole MerlotModel forward with `resnet_layers` set (pytest -m gpu)."""
+import pytest
+import torch
+
+from oracle import merlot_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from merlot_b200 import ops as o
+    return o
+
+
+def test_weight_standardisation(ops):  # utils/vision_transformer.py:56-60
+    g = torch.Generator().manual_seed(0)
+    for kh, cin, cout in ((3, 3, 32), (3, 64, 64), (1, 256, 128)):
+        w = torch.randn(kh, kh, cin, cout, generator=g) * 0.2 + 0.05
+        rows = kh * kh * cin
+        kp = (rows + 7) // 8 * 8
+        out = ops.ws_weights(w.reshape(rows, cout).to(DEV), kp).float().cpu()
+        mean = w.mean((0, 1, 2), keepdim=True)
+        ref = ((w - mean) * torch.rsqrt(((w - mean) ** 2).mean((0, 1, 2), keepdim=True) + 1e-5)).reshape(rows, cout)
+        assert rel(out[:rows], ref) < 4e-3                       # one bf16 rounding of the standardised kernel
+        assert torch.all(out[rows:] == 0) and out.shape == (kp, cout)
+
+
+@pytest.mark.parametrize("N,h,w,cin,cout,stride", [(2, 9, 7, 32, 64, 1), (1, 16, 24, 64, 64, 1), (2, 32, 48, 3, 32, 2), (1, 9, 7, 3, 32, 2)])
+def test_conv3x3_as_im2col_gemm(ops, N, h, w, cin, cout, stride):  # conv2d_fixed_padding :30-66 (SAME / fixed_padding + VALID)
+    g = torch.Generator().manual_seed(h * w + cin)
+    first = cin == 3  # the image conv subtracts 0.5 before the zero padding (:193)
+    x = (torch.rand(N, h, w, cin, generator=g) if first else torch.randn(N, h, w, cin, generator=g)).bfloat16()
+    k = (torch.randn(3, 3, cin, cout, generator=g) * 0.2).bfloat16()
+    rows = 9 * cin
+    kp = (rows + 7) // 8 * 8
+    ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+    col = torch.empty(N * ho * wo, kp, dtype=torch.bfloat16, device=DEV)
+    ops.im2col3x3(x.to(DEV), N, h, w, cin, stride, col, sub_half=first)
+    wmat = torch.zeros(kp, cout, dtype=torch.bfloat16)
+    wmat[:rows] = k.reshape(rows, cout)
+    y = ops.gemm(col, wmat.to(DEV), b_mn_major=True, out_dtype=torch.float32)
+    xin = (x.float() - 0.5).bfloat16().float() if first else x.float()
+    ref = O.conv2d_fixed_padding(xin, k.float(), strides=stride, weight_standardization=False)
+    assert tuple(ref.shape) == (N, ho, wo, cout)
+    assert rel(y, ref.reshape(N * ho * wo, cout)) < 2e-3
+
+
+@pytest.mark.parametrize("N,HW,C", [(2, 35, 32), (3, 63, 64), (2, 24, 256), (1, 7, 1024)])
+def test_group_norm_relu_shortcut(ops, N, HW, C):  # batch_norm_relu :22-27, bottleneck tail :95-96
+    g = torch.Generator().manual_seed(C)
+    x = (torch.randn(N, HW, 1, C, generator=g) * 1.5 + 0.3).bfloat16()
+    sc = torch.randn(N, HW, 1, C, generator=g).bfloat16()
+    p = {"s/gamma": torch.randn(C, generator=g) * 0.3 + 1.0, "s/beta": torch.randn(C, generator=g) * 0.2}
+    ref = O.group_norm(x.float(), p, "s")
+    stats = torch.empty(N * 64, device=DEV)
+    for relu, short in ((True, None), (False, None), (True, sc)):
+        y = torch.empty(N * HW, C, dtype=torch.bfloat16, device=DEV)
+        ops.group_norm_fwd(x.reshape(N * HW, C).to(DEV), p["s/gamma"].to(DEV), p["s/beta"].to(DEV), y, stats, N, HW, C, 32, 1e-4, relu,
+                           None if short is None else short.reshape(N * HW, C).to(DEV))
+        r = ref if short is None else ref.bfloat16().float() + short.float()
+        r = torch.relu(r) if relu else r
+        assert rel(y, r.reshape(N * HW, C)) < 6e-3
+
+
+def test_avgpool_same_ragged(ops):  # tf.nn.avg_pool2d SAME, odd sizes: bottom/right cells average fewer pixels
+    g = torch.Generator().manual_seed(2)
+    for N, h, w, C in ((2, 9, 7, 32), (1, 12, 22, 64)):
+        x = torch.randn(N, h, w, C, generator=g).bfloat16()
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        y = torch.empty(N * ho * wo, C, dtype=torch.bfloat16, device=DEV)
+        ops.avgpool2_same(x.to(DEV), N, h, w, C, y)
+        assert rel(y, O.avg_pool_same(x.float(), 2).reshape(N * ho * wo, C)) < 4e-3
+
+
+def _stem_cfg(tiny_cfg):
+    return dict(tiny_cfg, resnet_layers=[1, 2, 1], hidden_dropout_prob=0.0)
+
+
+def test_hybrid_stem_and_model_forward(tiny_cfg):
+    """lite_resnet50 + conv_postresnet_proj inside the MerlotModel forward (is_training=False) against the oracle on the same
+    weights; training through the stem is refused loudly."""
+    from merlot_b200.modeling import MerlotModel
+    from tests.test_gpu_model import build, synth
+    cfg = _stem_cfg(tiny_cfg)
+    batch, nc, Lc = 2, 2, 16
+    image, ids, shuf, vid = synth(cfg, batch, nc, Lc, 64, 96, 0)
+    params, store, _ = build(cfg)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=False,
+                    shuffled_idx_img=shuf.to(DEV), params=store)
+    N = batch * nc
+    rc, hs, ws = m._hybrid_stem(image.bfloat16().to(DEV).contiguous(), N, 64, 96)
+    ref = O.lite_resnet50(image - 0.5, params, "vision_backbone/vision_transformer/resnet50lite", cfg["resnet_layers"])
+    assert (hs, ws) == (4, 6) and tuple(ref.shape) == (N, 4, 6, 1024)
+    assert rel(rc, ref.reshape(N * 24, 1024)) < 3e-2          # ~20 bf16 convs + GroupNorms deep
+    om = O.MerlotOracle(cfg, params, image, ids, mask_input=False, shuffled_idx_img=shuf)
+    for name in ("viz", "lang"):
+        assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 3e-2
+    mt = MerlotModel(cfg, is_training=True, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                     shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=O.make_mask_draws(2, 32, 6, cfg["vocab_size"], seed=5))
+    mt.mask_loss()
+    with pytest.raises(NotImplementedError, match="hybrid ResNet-lite stem"):
+        mt.backward()

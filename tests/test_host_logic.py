@@ -43,10 +43,27 @@ def test_bench_config_equals_reference_yaml():
     assert cfg.optimizer == gold["optimizer"]
 
 
-def test_hybrid_stem_is_refused_loudly():
+def test_hybrid_stem_param_arena(tiny_cfg):
+    """merlot.yaml as shipped selects the hybrid ResNet-lite stem: the store holds its 164 variables under the reference's
+    names (conv kernels flattened [kh*kw*cin, cout]) and round-trips them HWIO against the oracle's independent name walk."""
+    from oracle import merlot_oracle as O
+    cfg = dict(tiny_cfg, resnet_layers=[1, 2, 1], patch_size=16)
+    st = ParamStore(cfg, device="cpu")
+    params = O.init_params(cfg, seed=0, perturb=0.1)
+    st.load_tf_dict(params)
+    back = st.to_tf_dict("p")
+    assert set(back) == set(params)
+    for k in params:
+        assert back[k].shape == params[k].shape and torch.equal(back[k], params[k]), k
+    vt = "vision_backbone/vision_transformer"
+    assert f"{vt}/conv2d/kernel" not in st.entries and f"{vt}/conv_postresnet_proj/kernel" in st.entries
+    assert st.entries[f"{vt}/resnet50lite/block_group2/conv2d_2/kernel"].shape == (9 * 128, 128)
+    gn = st.entries[f"{vt}/resnet50lite/stem/GroupNorm_stem0/gamma"]
+    assert gn.hyper[1] == 0.0  # "GroupNorm" matches the weight-decay-0 override (optimization.py:125-147)
     gold = json.load(open(os.path.join(HERE, "golden", "reference_facts.json")))["configs"]["merlot.yaml"]
-    with pytest.raises(NotImplementedError, match="ResNet"):
-        ParamStore(gold["model"], device="cpu")
+    from merlot_b200.params import stem_variables
+    n_stem = sum(int(torch.tensor(s_).prod()) for _, s_ in stem_variables(vt, gold["model"]["resnet_layers"], 64, 768))
+    assert n_stem == 11_914_080 + 1024 * 768 + 768  # SURVEY Appendix D: 11.91 M + 0.79 M
 
 
 def test_param_arena_roundtrip_and_count(tiny_cfg):
