@@ -144,7 +144,18 @@ def transformer(hidden, mask, p: Params, scope: str, num_layers: int, heads: int
 # Restated ahead of the CUDA path so that path starts with a checker; merlot_b200 still raises NotImplementedError
 # for resnet_layers != [].
 # ------------------------------------------------------------------------------------------------------------
-def group_norm(x: torch.Tensor, p: Params, scope: str, num_groups: int = 32, eps: float = 1e-4) -> torch.Tensor:
+def _ident(t: torch.Tensor) -> torch.Tensor:
+    return t
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    """Pass as `rnd=` to the stem functions to materialise every tensor the reference holds in bfloat16 (conv operands and
+    outputs, the cast standardised kernel :62-63, GroupNorm outputs model_utils.py:219-220, pooled maps, residual sums) with
+    bf16 rounding, i.e. the reference's own precision policy instead of the fp32 restatement."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def group_norm(x: torch.Tensor, p: Params, scope: str, num_groups: int = 32, eps: float = 1e-4, rnd=_ident) -> torch.Tensor:
     """utils/model_utils.py:133-222 as called by batch_norm_relu (vision_transformer.py:22-27): NHWC, 32 groups, eps 1e-4,
     mean_close_to_zero=True => ONE-PASS moments (sufficient_statistics + normalize_moments, :196-201):
     mean = sum(x)/n, var = sum(x^2)/n - mean^2 over (h, w, channels-in-group) per (sample, group); gamma/beta per channel."""
@@ -156,10 +167,11 @@ def group_norm(x: torch.Tensor, p: Params, scope: str, num_groups: int = 32, eps
     mean = xr.sum((1, 2, 4), keepdim=True) / cnt
     var = (xr * xr).sum((1, 2, 4), keepdim=True) / cnt - mean * mean
     y = ((xr - mean) * torch.rsqrt(var + eps)).reshape(n, h, w, c)
-    return y * p[f"{scope}/gamma"] + p[f"{scope}/beta"]
+    return rnd(y * p[f"{scope}/gamma"] + p[f"{scope}/beta"])
 
 
-def conv2d_fixed_padding(x: torch.Tensor, kernel: torch.Tensor, strides: int = 1, weight_standardization: bool = True) -> torch.Tensor:
+def conv2d_fixed_padding(x: torch.Tensor, kernel: torch.Tensor, strides: int = 1, weight_standardization: bool = True,
+                         rnd=_ident) -> torch.Tensor:
     """vision_transformer.py:30-66.  x NHWC, kernel HWIO, no bias.  strides > 1: explicit pad (k-1)//2 before / the rest after
     (fixed_padding :8-19) then VALID; strides == 1: SAME.  Weight standardisation (:56-60): per OUTPUT channel, moments over
     (kh, kw, cin), biased variance, eps 1e-5."""
@@ -168,6 +180,7 @@ def conv2d_fixed_padding(x: torch.Tensor, kernel: torch.Tensor, strides: int = 1
         mean = kernel.mean((0, 1, 2), keepdim=True)
         var = ((kernel - mean) ** 2).mean((0, 1, 2), keepdim=True)
         kernel = (kernel - mean) * torch.rsqrt(var + 1e-5)
+    kernel = rnd(kernel)
     xn = x.permute(0, 3, 1, 2)
     if strides > 1:
         beg = (k - 1) // 2
@@ -176,13 +189,13 @@ def conv2d_fixed_padding(x: torch.Tensor, kernel: torch.Tensor, strides: int = 1
     else:
         assert k % 2 == 1
         y = F.conv2d(xn, kernel.permute(3, 2, 0, 1), padding=k // 2)
-    return y.permute(0, 2, 3, 1)
+    return rnd(y.permute(0, 2, 3, 1))
 
 
-def avg_pool_same(x: torch.Tensor, s: int) -> torch.Tensor:
+def avg_pool_same(x: torch.Tensor, s: int, rnd=_ident) -> torch.Tensor:
     """tf.nn.avg_pool2d(ksize=s, strides=s, padding='SAME') on NHWC: ceil(h/s) outputs, padding at the bottom/right only,
     padded cells excluded from the average."""
-    return F.avg_pool2d(x.permute(0, 3, 1, 2), s, s, ceil_mode=True, count_include_pad=False).permute(0, 2, 3, 1)
+    return rnd(F.avg_pool2d(x.permute(0, 3, 1, 2), s, s, ceil_mode=True, count_include_pad=False).permute(0, 2, 3, 1))
 
 
 class _ScopeNames:
@@ -205,34 +218,36 @@ class _ScopeNames:
         return f"{self.scope}/{n}"
 
 
-def bottleneck_block(x: torch.Tensor, p: Params, names: _ScopeNames, filters: int, strides: int, use_projection: bool) -> torch.Tensor:
+def bottleneck_block(x: torch.Tensor, p: Params, names: _ScopeNames, filters: int, strides: int, use_projection: bool,
+                     rnd=_ident) -> torch.Tensor:
     """vision_transformer.py:69-96.  Striding is done by average pooling: the shortcut pools BEFORE its 1x1 (:79-83), the main
     path pools AFTER the 3x3 (:92-93).  Variable creation order: [shortcut conv, GN], 1x1, GN, 3x3, GN, 1x1, GN."""
     shortcut = x
     if use_projection:
-        sc_in = avg_pool_same(x, strides) if strides > 1 else x
-        shortcut = group_norm(conv2d_fixed_padding(sc_in, p[names.conv()]), p, names.gn())  # skip_relu=True
-    y = torch.relu(group_norm(conv2d_fixed_padding(x, p[names.conv()]), p, names.gn()))
-    y = torch.relu(group_norm(conv2d_fixed_padding(y, p[names.conv()]), p, names.gn()))
+        sc_in = avg_pool_same(x, strides, rnd) if strides > 1 else x
+        shortcut = group_norm(conv2d_fixed_padding(sc_in, p[names.conv()], rnd=rnd), p, names.gn(), rnd=rnd)  # skip_relu=True
+    y = torch.relu(group_norm(conv2d_fixed_padding(x, p[names.conv()], rnd=rnd), p, names.gn(), rnd=rnd))
+    y = torch.relu(group_norm(conv2d_fixed_padding(y, p[names.conv()], rnd=rnd), p, names.gn(), rnd=rnd))
     if strides > 1:
-        y = avg_pool_same(y, strides)
-    y = group_norm(conv2d_fixed_padding(y, p[names.conv()]), p, names.gn())  # skip_relu=True
-    return torch.relu(y + shortcut)
+        y = avg_pool_same(y, strides, rnd)
+    y = group_norm(conv2d_fixed_padding(y, p[names.conv()], rnd=rnd), p, names.gn(), rnd=rnd)  # skip_relu=True
+    return torch.relu(rnd(y + shortcut))
 
 
-def lite_resnet50(x: torch.Tensor, p: Params, scope: str, layers, width: int = 64) -> torch.Tensor:
+def lite_resnet50(x: torch.Tensor, p: Params, scope: str, layers, width: int = 64, rnd=_ident) -> torch.Tensor:
     """vision_transformer.py:118-170: 3-conv stem (3x3 s2, 3x3, 3x3; GN+ReLU each) -> avg-pool 2 -> len(layers) block groups
     with filters width*2^i, stride 1 for the first group and 2 after."""
     st = _ScopeNames(f"{scope}/stem")
-    x0 = torch.relu(group_norm(conv2d_fixed_padding(x, p[st.conv()], strides=2), p, st.gn("stem0")))
-    x1 = torch.relu(group_norm(conv2d_fixed_padding(x0, p[st.conv()]), p, st.gn("stem1")))
-    x2 = torch.relu(group_norm(conv2d_fixed_padding(x1, p[st.conv()]), p, st.gn("stem2")))
-    c = avg_pool_same(x2, 2)
+    x = rnd(x)
+    x0 = torch.relu(group_norm(conv2d_fixed_padding(x, p[st.conv()], strides=2, rnd=rnd), p, st.gn("stem0"), rnd=rnd))
+    x1 = torch.relu(group_norm(conv2d_fixed_padding(x0, p[st.conv()], rnd=rnd), p, st.gn("stem1"), rnd=rnd))
+    x2 = torch.relu(group_norm(conv2d_fixed_padding(x1, p[st.conv()], rnd=rnd), p, st.gn("stem2"), rnd=rnd))
+    c = avg_pool_same(x2, 2, rnd)
     for i, blocks in enumerate(layers):
         names = _ScopeNames(f"{scope}/block_group{i + 1}")
-        c = bottleneck_block(c, p, names, width * (2 ** i), 1 if i == 0 else 2, True)  # :109-110
+        c = bottleneck_block(c, p, names, width * (2 ** i), 1 if i == 0 else 2, True, rnd)  # :109-110
         for _ in range(1, blocks):
-            c = bottleneck_block(c, p, names, width * (2 ** i), 1, False)
+            c = bottleneck_block(c, p, names, width * (2 ** i), 1, False, rnd)
     return c
 
 
