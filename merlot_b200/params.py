@@ -256,9 +256,16 @@ class ParamStore:
             ops.cast_f32_to_bf16(self.p, self.pb)
 
     # ---- interop with the reference's variable names ----
-    def load_tf_dict(self, d: Dict[str, torch.Tensor]):
+    def load_tf_dict(self, d: Dict[str, torch.Tensor], strict: bool = True):
+        """Copy reference-named variables into the arena.  strict=False applies the reference's init-from-checkpoint rule
+        (utils/model_utils.py:388-413): a variable is restored iff the checkpoint has it, everything else keeps its current
+        value; returns the list of entries that were NOT found."""
+        missing = []
         with torch.no_grad():
             for e in self.entries.values():
+                if not strict and not all(t in d for t in e.tf_names):
+                    missing.append(e.name)
+                    continue
                 dst = self.P(e.name)
                 if len(e.tf_names) == 3:
                     src = torch.cat([d[t] for t in e.tf_names], dim=-1)
@@ -269,6 +276,12 @@ class ParamStore:
                     src = d[e.tf_names[0]].reshape(e.shape)
                 dst.copy_(src.to(torch.float32))
         self.sync_bf16()
+        return missing
+
+    def load_checkpoint(self, prefix: str):
+        """`init_checkpoint` (model/modeling.py:724-740): restore by name from a TensorFlow V2 checkpoint prefix."""
+        from .tf_checkpoint import load_checkpoint
+        return self.load_tf_dict(load_checkpoint(prefix), strict=False)
 
     def to_tf_dict(self, which: str = "p") -> Dict[str, torch.Tensor]:
         buf = {"p": self.p, "g": self.g}[which]
