@@ -114,3 +114,30 @@ def avg_pool_same(x, s):  # tf.nn.avg_pool2d SAME, ksize = strides = s: bottom/r
         for j in range(wo):
             out[:, i, j] = x[:, i * s:min(h, (i + 1) * s), j * s:min(w, (j + 1) * s)].mean((1, 2))
     return out
+
+
+# ---- batch-level input step (model/dataloader.py:210-272), written independently of merlot_b200/dataloader.py ---------------
+def process_example_np(input_ids, video_src_ids, chunk_u, num_shuffle, pick_u, order_u, num_chunks_in_group, shuffle_prob,
+                       shuffle_chunks):
+    """Returns (permutation idx [b, n] applied to every per-chunk feature, shuffled_idx_img [B*g]).  tf.argsort of distinct
+    values == np.argsort(kind='stable')."""
+    b, n = video_src_ids.shape
+    idx = np.tile(np.arange(n), (b, 1))
+    if shuffle_chunks:
+        idx = np.empty((b, n), dtype=np.int64)
+        for r in range(b):
+            mapping = np.argsort(chunk_u[r], kind="stable")          # chunkid_to_new_id_mapping (:216)
+            new_chunkid = mapping[video_src_ids[r]]                   # (:217)
+            trg = new_chunkid * n + np.arange(n)                      # (:218)
+            idx[r] = np.argsort(trg, kind="stable")                   # (:219)
+    g = num_chunks_in_group
+    B = b * n // g
+    out = np.tile(np.arange(g, dtype=np.int32), (B, 1))
+    if shuffle_prob >= 1e-6:
+        for r in range(B):
+            rank = np.argsort(pick_u[r], kind="stable")               # (:251): argsort VALUES compared with the count
+            order = np.argsort(order_u[r], kind="stable")
+            for j in range(g):
+                if rank[j] < num_shuffle[r]:
+                    out[r, j] = 16 + order[j]
+    return idx, out.reshape(-1)

@@ -106,3 +106,52 @@ def test_no_cpu_fallback():
     from merlot_b200 import ops
     with pytest.raises(_lib.MerlotError):
         ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batch-level input step (model/dataloader.py:210-272): integer results bit-exact vs NumPy
+# ---------------------------------------------------------------------------------------------------------------
+def test_process_example_matches_numpy_restatement():
+    import numpy as np
+    from merlot_b200 import dataloader as D
+    from oracle import oracle_np as N
+    b, n, g, L = 3, 8, 4, 5
+    gen = torch.Generator().manual_seed(0)
+    feats = {
+        "images": torch.rand(b, n, 4, 6, 3, generator=gen),
+        "input_ids": torch.randint(0, 1000, (b, n, L), generator=gen, dtype=torch.int32),
+        "video_src_ids": torch.tensor([[0, 0, 0, 0, 1, 1, 2, 2], [0, 0, 0, 0, 0, 0, 0, 0], [0, 1, 1, 1, 1, 2, 2, 2]], dtype=torch.int32),
+        "chunk_num": torch.arange(b * n, dtype=torch.int32).reshape(b, n),
+    }
+    model_cfg = {"num_chunks_in_group": g, "image_shuffle_prob": 0.4, "transpose_input": True}
+    for seed in range(5):
+        draws = D.make_draws(b, n, g, 0.4, seed)
+        out = D.process_example(feats, {"shuffle_chunks": True}, model_cfg, is_training=True, draws=draws)
+        idx, shuf = N.process_example_np(feats["input_ids"].numpy(), feats["video_src_ids"].numpy(), draws["chunk_u"].numpy(),
+                                         draws["num_shuffle"].numpy(), draws["pick_u"].numpy(), draws["order_u"].numpy(), g, 0.4, True)
+        assert np.array_equal(out["shuffled_idx_img"].numpy(), shuf)
+        for r in range(b):
+            assert np.array_equal(out["input_ids"][r].numpy(), feats["input_ids"][r].numpy()[idx[r]])
+            assert np.array_equal(out["chunk_num"][r].numpy(), feats["chunk_num"][r].numpy()[idx[r]])
+            vs = out["video_src_ids"][r].tolist()  # whole videos move together and keep their internal order (:212-213)
+            assert all(vs.count(v) == feats["video_src_ids"][r].tolist().count(v) for v in set(vs))
+            assert [k for k, _ in __import__("itertools").groupby(vs)] == list(dict.fromkeys(vs))
+            for v in set(vs):
+                pos = [i for i, q in enumerate(vs) if q == v]
+                assert out["chunk_num"][r][pos].tolist() == sorted(out["chunk_num"][r][pos].tolist())
+        img = out["images"]
+        assert tuple(img.shape) == (4, 6, 3, b * n)  # flattened, then [h, w, 3, N] for the TPU-friendly transpose (:262-264)
+        flat = img.permute(3, 0, 1, 2)
+        assert torch.equal(flat[1 * n + 2], feats["images"][1][idx[1][2]])
+        s = out["shuffled_idx_img"].reshape(b * n // g, g)
+        for row, k in zip(s.tolist(), draws["num_shuffle"].tolist()):
+            moved = [v for v in row if v >= 16]
+            assert len(moved) == k and len(set(moved)) == k and all(16 <= v < 16 + g for v in moved)
+            assert all(v == j for j, v in enumerate(row) if v < 16)
+    # no shuffling at all: identity ids, images only flattened in eval mode
+    out = D.process_example(feats, {}, {"num_chunks_in_group": g, "image_shuffle_prob": 0.0}, is_training=False)
+    assert out["shuffled_idx_img"].tolist() == list(range(g)) * (b * n // g) and tuple(out["images"].shape) == (b * n, 4, 6, 3)
+    assert torch.equal(out["input_ids"], feats["input_ids"])
+    assert D.num_shuffle_probs(4, 0.4)[:2] == [0.6, 1e-6] and abs(D.expected_out_of_place(4, 0.4) - (1.2 + 1e-6)) < 1e-12
+    with pytest.raises(ValueError):
+        D.process_example({**feats, "input_ids": feats["input_ids"][:, :7]}, {}, model_cfg)
