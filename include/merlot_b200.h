@@ -316,6 +316,20 @@ int merlot_group_norm_fwd(const void* x_bf16, const float* gamma, const float* b
 /* tf.nn.avg_pool2d(ksize 2, strides 2, 'SAME') on NHWC bf16 (:81,93,159) */
 int merlot_avgpool2_same(const void* x_bf16, int N, int h, int w, int C, void* y_bf16, void* stream);
 
+/* K13 backward pieces (tf.gradients of the same graph; UNVERIFIED ON HARDWARE at the end of round 1: the host keeps them
+ * behind MERLOT_STEM_BACKWARD=1 and tests/test_gpu_stem.py gates their tests on the same variable) */
+/* GroupNorm(+ReLU, +shortcut) backward: g = dy * [y > 0]; dx, dshortcut (= g, optional), dgamma += , dbeta += ;
+ * red: f32 scratch [N, groups, 2]; stats: what merlot_group_norm_fwd left for this site */
+int merlot_group_norm_bwd(const void* dy_bf16, const void* x_bf16, const void* y_bf16, const float* stats, const float* gamma,
+                          void* dx_bf16, void* dshortcut_bf16, float* dgamma, float* dbeta, float* red, int N, int HW, int C,
+                          int groups, float eps, int relu, void* stream);
+int merlot_avgpool2_same_bwd(const void* dy_bf16, int N, int h, int w, int C, void* dx_bf16, void* stream);
+/* adjoint of merlot_im2col3x3: dx[N,h,w,C] = sum of the taps of dcol [N*ho*wo, ld] that read each pixel */
+int merlot_col2im3x3(const void* dcol_bf16, int N, int h, int w, int C, int stride, int ld, void* dx_bf16, void* stream);
+/* weight-standardisation backward: dw[rows, cout] += d(standardise)/dw applied to dws[rows(, ld), cout] */
+int merlot_ws_weights_bwd(const float* dws, int ld_dws, const float* w, int rows, int cout, float* dw, void* stream);
+int merlot_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
+
 /* bench.py roofline support: time every K1 launch with CUDA events on its own stream between begin/end.
  * end() synchronises the device and returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count. */
 void merlot_gemm_profile_begin(void);

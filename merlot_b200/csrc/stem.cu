@@ -176,6 +176,216 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const bf16* __restrict__ 
                  pack_bf16x2(a[6] * inv, a[7] * inv));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// backward pieces (gradient of the same graph; vision_transformer.py has no explicit backward -- tf.gradients derives it)
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm(+ReLU / +shortcut) backward, pass 1: with g = dy * [y > 0] (when relu) and xhat = (x - mean) * rstd,
+//   red[n][grp] += { sum g*gamma, sum g*gamma*xhat }   (group sums for dx),   dgamma[c] += sum g*xhat,   dbeta[c] += sum g
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const bf16* __restrict__ y, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, int HW, int C, int groups, float eps,
+                                                            int relu, int rows_per_block, float* __restrict__ red,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float acc[];  // [groups][2]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int c8n = C >> 3;
+  const int lanes = blockDim.x / c8n > 0 ? blockDim.x / c8n : 1;
+  const int c8 = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(HW, r0 + rows_per_block);
+  const int cg = C / groups;
+  const float inv_cnt = 1.0f / ((float)HW * (float)cg);
+  if (rl < lanes) {
+    float mean[8], rstd[8], gm[8], s1[8], s2[8], dg[8], db[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c8 * 8 + i;
+      const int g = c / cg;
+      mean[i] = stats[((size_t)n * groups + g) * 2] * inv_cnt;
+      rstd[i] = rsqrtf(stats[((size_t)n * groups + g) * 2 + 1] * inv_cnt - mean[i] * mean[i] + eps);
+      gm[i] = gamma[c];
+      s1[i] = s2[i] = dg[i] = db[i] = 0.f;
+    }
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const size_t off = ((size_t)n * HW + r) * C + c8 * 8;
+      const uint4 du = *reinterpret_cast<const uint4*>(dy + off);
+      const uint4 xu = *reinterpret_cast<const uint4*>(x + off);
+      uint4 yu = make_uint4(0u, 0u, 0u, 0u);
+      if (relu) yu = *reinterpret_cast<const uint4*>(y + off);
+      const uint32_t dw[4] = {du.x, du.y, du.z, du.w}, xw[4] = {xu.x, xu.y, xu.z, xu.w}, yw[4] = {yu.x, yu.y, yu.z, yu.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 d2 = unpack_bf16x2(dw[i]), x2 = unpack_bf16x2(xw[i]), y2 = unpack_bf16x2(yw[i]);
+        const float gv[2] = {(!relu || y2.x > 0.f) ? d2.x : 0.f, (!relu || y2.y > 0.f) ? d2.y : 0.f};
+        const float xv[2] = {x2.x, x2.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = 2 * i + j;
+          const float xh = (xv[j] - mean[k]) * rstd[k];
+          s1[k] += gv[j] * gm[k];
+          s2[k] += gv[j] * gm[k] * xh;
+          dg[k] += gv[j] * xh;
+          db[k] += gv[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c8 * 8 + i;
+      const int g = c / cg;
+      atomicAdd(&acc[2 * g], s1[i]);
+      atomicAdd(&acc[2 * g + 1], s2[i]);
+      atomicAdd(&dgamma[c], dg[i]);
+      atomicAdd(&dbeta[c], db[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&red[(size_t)n * 2 * groups + i], acc[i]);
+}
+
+// pass 2: dx = rstd * (g*gamma - S1/cnt - xhat * S2/cnt);  dshortcut = g (the residual branch sees the masked gradient)
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                           const bf16* __restrict__ y, const float* __restrict__ stats,
+                                                           const float* __restrict__ red, const float* __restrict__ gamma,
+                                                           bf16* __restrict__ dx, bf16* __restrict__ dshortcut, int HW, int C, int groups,
+                                                           float eps, int relu, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long row = idx / c8n;
+  const int n = (int)(row / HW);
+  const int cg = C / groups;
+  const float inv_cnt = 1.0f / ((float)HW * (float)cg);
+  const size_t off = (size_t)row * C + c8 * 8;
+  const uint4 du = *reinterpret_cast<const uint4*>(dy + off);
+  const uint4 xu = *reinterpret_cast<const uint4*>(x + off);
+  uint4 yu = make_uint4(0u, 0u, 0u, 0u);
+  if (relu) yu = *reinterpret_cast<const uint4*>(y + off);
+  const uint32_t dw[4] = {du.x, du.y, du.z, du.w}, xw[4] = {xu.x, xu.y, xu.z, xu.w}, yw[4] = {yu.x, yu.y, yu.z, yu.w};
+  float o[8], gsc[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 d2 = unpack_bf16x2(dw[i]), x2 = unpack_bf16x2(xw[i]), y2 = unpack_bf16x2(yw[i]);
+    const float gv[2] = {(!relu || y2.x > 0.f) ? d2.x : 0.f, (!relu || y2.y > 0.f) ? d2.y : 0.f};
+    const float xv[2] = {x2.x, x2.y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = 2 * i + j;
+      const int c = c8 * 8 + k;
+      const int g = c / cg;
+      const float mean = stats[((size_t)n * groups + g) * 2] * inv_cnt;
+      const float rstd = rsqrtf(stats[((size_t)n * groups + g) * 2 + 1] * inv_cnt - mean * mean + eps);
+      const float xh = (xv[j] - mean) * rstd;
+      const float S1 = red[((size_t)n * groups + g) * 2] * inv_cnt, S2 = red[((size_t)n * groups + g) * 2 + 1] * inv_cnt;
+      o[k] = rstd * (gv[j] * gamma[c] - S1 - xh * S2);
+      gsc[k] = gv[j];
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + off) =
+      make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  if (dshortcut != nullptr)
+    *reinterpret_cast<uint4*>(dshortcut + off) =
+        make_uint4(pack_bf16x2(gsc[0], gsc[1]), pack_bf16x2(gsc[2], gsc[3]), pack_bf16x2(gsc[4], gsc[5]), pack_bf16x2(gsc[6], gsc[7]));
+}
+
+// avg-pool backward: every input pixel receives dy / (number of valid pixels in its window)
+__global__ void __launch_bounds__(256) avgpool2_bwd_kernel(const bf16* __restrict__ dy, int N, int h, int w, int C, int ho, int wo,
+                                                           bf16* __restrict__ dx, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long row = idx / c8n;
+  const int ix = (int)(row % w), iy = (int)((row / w) % h), n = (int)(row / ((long long)w * h));
+  const int oy = iy >> 1, ox = ix >> 1;
+  const int cnt = ((oy * 2 + 1 < h) ? 2 : 1) * ((ox * 2 + 1 < w) ? 2 : 1);
+  const float inv = 1.0f / (float)cnt;
+  const uint4 u = *reinterpret_cast<const uint4*>(dy + (((size_t)n * ho + oy) * wo + ox) * C + c8 * 8);
+  const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(wv[i]); a[2 * i] = f.x * inv; a[2 * i + 1] = f.y * inv; }
+  *reinterpret_cast<uint4*>(dx + (size_t)row * C + c8 * 8) =
+      make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+}
+
+// col2im for the 3x3 taps: dx[n, iy, ix, :] = sum over taps of dcol[row(oy, ox), tap*C : tap*C + C] with oy*stride + ky - 1 == iy
+__global__ void __launch_bounds__(256) col2im3x3_kernel(const bf16* __restrict__ dcol, int N, int h, int w, int C, int stride, int ho,
+                                                        int wo, int ld, bf16* __restrict__ dx, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long pix = idx / c8n;
+  const int ix = (int)(pix % w), iy = (int)((pix / w) % h), n = (int)(pix / ((long long)w * h));
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ty = iy - ky + 1;
+    if (ty < 0 || ty % stride != 0) continue;
+    const int oy = ty / stride;
+    if (oy >= ho) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int tx = ix - kx + 1;
+      if (tx < 0 || tx % stride != 0) continue;
+      const int ox = tx / stride;
+      if (ox >= wo) continue;
+      const uint4 u = *reinterpret_cast<const uint4*>(dcol + (((size_t)n * ho + oy) * wo + ox) * ld + (ky * 3 + kx) * C + c8 * 8);
+      const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(wv[i]); a[2 * i] += f.x; a[2 * i + 1] += f.y; }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + (size_t)pix * C + c8 * 8) =
+      make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+}
+
+// weight-standardisation backward, per output channel: what = (w - mean) * rstd,
+//   dw += rstd * (dws - mean_r(dws) - what * mean_r(dws * what))
+__global__ void __launch_bounds__(256) ws_bwd_kernel(const float* __restrict__ dws, int ld_dws, const float* __restrict__ w, int rows,
+                                                     int cout, float* __restrict__ dw) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  float mean = 0.f;
+  for (int r = 0; r < rows; ++r) mean += w[(size_t)r * cout + c];
+  mean /= (float)rows;
+  float var = 0.f;
+  for (int r = 0; r < rows; ++r) { const float d = w[(size_t)r * cout + c] - mean; var += d * d; }
+  var /= (float)rows;
+  const float rstd = rsqrtf(var + 1e-5f);
+  float m1 = 0.f, m2 = 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float g = dws[(size_t)r * ld_dws + c];
+    m1 += g;
+    m2 += g * (w[(size_t)r * cout + c] - mean) * rstd;
+  }
+  m1 /= (float)rows;
+  m2 /= (float)rows;
+  for (int r = 0; r < rows; ++r) {
+    const float wh = (w[(size_t)r * cout + c] - mean) * rstd;
+    dw[(size_t)r * cout + c] += rstd * (dws[(size_t)r * ld_dws + c] - m1 - wh * m2);
+  }
+}
+
+__global__ void __launch_bounds__(256) add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
+                                                       long long n8) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const uint4 ua = *reinterpret_cast<const uint4*>(a + idx * 8), ub = *reinterpret_cast<const uint4*>(b + idx * 8);
+  const uint32_t aw[4] = {ua.x, ua.y, ua.z, ua.w}, bw[4] = {ub.x, ub.y, ub.z, ub.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = unpack_bf16x2(aw[i]), fb = unpack_bf16x2(bw[i]);
+    o[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -238,6 +448,70 @@ extern "C" int merlot_avgpool2_same(const void* x_bf16, int N, int h, int w, int
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   const long long total = (long long)N * ho * wo * (C / 8);
   avgpool2_kernel<<<GRID1D(total)>>>((const bf16*)x_bf16, N, h, w, C, ho, wo, (bf16*)y_bf16, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_group_norm_bwd(const void* dy_bf16, const void* x_bf16, const void* y_bf16, const float* stats, const float* gamma,
+                                     void* dx_bf16, void* dshortcut_bf16, float* dgamma, float* dbeta, float* red, int N, int HW, int C,
+                                     int groups, float eps, int relu, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(dy_bf16 && x_bf16 && stats && gamma && dx_bf16 && dgamma && dbeta && red, MERLOT_EINVAL, "group_norm_bwd: null pointer");
+  MB_REQUIRE(!relu || y_bf16, MERLOT_EINVAL, "group_norm_bwd: the ReLU mask needs the forward output y");
+  MB_REQUIRE(groups > 0 && C % groups == 0 && C % 8 == 0 && C / 8 <= 256, MERLOT_ESHAPE, "group_norm_bwd: bad C=%d groups=%d", C, groups);
+  if (N == 0 || HW == 0) return MERLOT_OK;
+  MB_CHECK_CUDA(cudaMemsetAsync(red, 0, sizeof(float) * 2 * (size_t)groups * N, st));
+  const int lanes = 256 / (C / 8);
+  int rows_per_block = lanes * 32;
+  if (rows_per_block > HW) rows_per_block = HW;
+  dim3 grid((unsigned)ceil_div(HW, rows_per_block), (unsigned)N);
+  gn_bwd_reduce_kernel<<<grid, 256, 2 * groups * sizeof(float), st>>>((const bf16*)dy_bf16, (const bf16*)x_bf16, (const bf16*)y_bf16, stats,
+                                                                      gamma, HW, C, groups, eps, relu, rows_per_block, red, dgamma, dbeta);
+  MB_CHECK_LAUNCH();
+  const long long total = (long long)N * HW * (C / 8);
+  gn_bwd_apply_kernel<<<GRID1D(total)>>>((const bf16*)dy_bf16, (const bf16*)x_bf16, (const bf16*)y_bf16, stats, red, gamma, (bf16*)dx_bf16,
+                                         (bf16*)dshortcut_bf16, HW, C, groups, eps, relu, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_avgpool2_same_bwd(const void* dy_bf16, int N, int h, int w, int C, void* dx_bf16, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(dy_bf16 && dx_bf16, MERLOT_EINVAL, "avgpool2_same_bwd: null pointer");
+  MB_REQUIRE(C % 8 == 0 && N > 0 && h > 0 && w > 0, MERLOT_ESHAPE, "avgpool2_same_bwd: C must be a multiple of 8 (got %d)", C);
+  const long long total = (long long)N * h * w * (C / 8);
+  avgpool2_bwd_kernel<<<GRID1D(total)>>>((const bf16*)dy_bf16, N, h, w, C, (h + 1) / 2, (w + 1) / 2, (bf16*)dx_bf16, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_col2im3x3(const void* dcol_bf16, int N, int h, int w, int C, int stride, int ld, void* dx_bf16, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(dcol_bf16 && dx_bf16, MERLOT_EINVAL, "col2im3x3: null pointer");
+  MB_REQUIRE(C % 8 == 0 && ld >= 9 * C && ld % 8 == 0 && (stride == 1 || stride == 2), MERLOT_ESHAPE,
+             "col2im3x3: C %% 8 == 0, ld >= 9*C, ld %% 8 == 0 and stride 1 or 2 required (C=%d ld=%d stride=%d)", C, ld, stride);
+  const int ho = (h + 2 - 3) / stride + 1, wo = (w + 2 - 3) / stride + 1;
+  const long long total = (long long)N * h * w * (C / 8);
+  col2im3x3_kernel<<<GRID1D(total)>>>((const bf16*)dcol_bf16, N, h, w, C, stride, ho, wo, ld, (bf16*)dx_bf16, total);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_ws_weights_bwd(const float* dws, int ld_dws, const float* w, int rows, int cout, float* dw, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(dws && w && dw, MERLOT_EINVAL, "ws_weights_bwd: null pointer");
+  MB_REQUIRE(rows > 0 && cout > 0 && ld_dws >= cout, MERLOT_ESHAPE, "ws_weights_bwd: bad shape rows=%d cout=%d ld=%d", rows, cout, ld_dws);
+  ws_bwd_kernel<<<GRID1D((long long)cout)>>>(dws, ld_dws, w, rows, cout, dw);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+extern "C" int merlot_add_bf16(const void* a, const void* b, void* out, long long n, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(a && b && out, MERLOT_EINVAL, "add_bf16: null pointer");
+  MB_REQUIRE(n % 8 == 0, MERLOT_ESHAPE, "add_bf16: n must be a multiple of 8");
+  if (n == 0) return MERLOT_OK;
+  add_bf16_kernel<<<GRID1D(n / 8)>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n / 8);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }

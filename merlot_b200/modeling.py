@@ -338,13 +338,16 @@ class MerlotModel(object):
         self._heads = {}
 
     def _hybrid_stem(self, img, N, h0, w0):
-        """lite_resnet50 (utils/vision_transformer.py:118-170), FORWARD only: NHWC bf16 activations as [N*h*w, C] matrices, every
-        conv a K1 GEMM on weight-standardised bf16 kernels (1x1: the activation matrix itself; 3x3: an im2col matrix), GroupNorm32
-        (+ReLU / +shortcut) and the avg-pool striding as K13 kernels (csrc/stem.cu).  Variables are consumed in the reference's
-        creation order (params.stem_variables).  Returns ([N*h*w, 4*f_last] bf16, h, w)."""
+        """lite_resnet50 (utils/vision_transformer.py:118-170): NHWC bf16 activations as [N*h*w, C] matrices, every conv a K1 GEMM
+        on weight-standardised bf16 kernels (1x1: the activation matrix itself; 3x3: an im2col matrix), GroupNorm32 (+ReLU /
+        +shortcut) and the avg-pool striding as K13 kernels (csrc/stem.cu).  Variables are consumed in the reference's creation
+        order (params.stem_variables).  With save_for_backward every op keeps its own buffers and is recorded on a tape for
+        _hybrid_stem_backward.  Returns ([N*h*w, 4*f_last] bf16, h, w)."""
         st, bf = self.store, self._bufs
         vt = "vision_backbone/vision_transformer"
-        stats = bf.get("stem.gn_stats", (N * 64,), torch.float32)
+        save = bool(getattr(self, "_save", False))
+        tape = []
+        site = [0]
 
         class _Names:  # tf default-name uniquification inside one variable scope
             def __init__(self, scope):
@@ -362,8 +365,9 @@ class MerlotModel(object):
                 self.ng += 1
                 return n
 
-        def T(tag, rows, cols):
-            return bf.get(f"stem.{tag}", (rows, cols), torch.bfloat16)
+        def T(tag, rows, cols):  # training: one buffer per op (the backward pass reads them); inference: reuse by tag and shape
+            site[0] += 1
+            return bf.get(f"stem.{tag}.{site[0]}" if save else f"stem.{tag}", (rows, cols), torch.bfloat16)
 
         def conv(x, h, w, cin, kname, k, tag, stride=1, sub_half=False):
             wk = st.P(kname)  # fp32 [k*k*cin, cout]
@@ -375,21 +379,26 @@ class MerlotModel(object):
                 a, ho, wo = x, h, w
             else:
                 ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
-                a = T("col", N * ho * wo, kp)
+                a = bf.get("stem.col", (N * ho * wo, kp), torch.bfloat16)  # recomputed in the backward pass: never per-op
                 ops.im2col3x3(x, N, h, w, cin, stride, a, sub_half=sub_half)
             y = T(tag, N * ho * wo, cout)
             ops.gemm(a, wstd, b_mn_major=True, out=y)
+            tape.append(("conv", dict(x=x, h=h, w=w, cin=cin, kname=kname, k=k, stride=stride, sub_half=sub_half, y=y, ho=ho, wo=wo,
+                                      cout=cout, kp=kp)))
             return y, ho, wo, cout
 
         def gn(x, hw, c, scope_name, tag, relu=True, shortcut=None):
             y = T(tag, N * hw, c)
+            stats = bf.get(f"stem.gn_stats.{site[0]}" if save else "stem.gn_stats", (N * 64,), torch.float32)
             ops.group_norm_fwd(x, st.P(f"{scope_name}/gamma"), st.P(f"{scope_name}/beta"), y, stats, N, hw, c, 32, 1e-4, relu, shortcut)
+            tape.append(("gn", dict(x=x, y=y, scope=scope_name, hw=hw, c=c, relu=relu, shortcut=shortcut, stats=stats)))
             return y
 
         def pool(x, h, w, c, tag):
             ho, wo = (h + 1) // 2, (w + 1) // 2
             y = T(tag, N * ho * wo, c)
             ops.avgpool2_same(x, N, h, w, c, y)
+            tape.append(("pool", dict(x=x, h=h, w=w, c=c, y=y)))
             return y, ho, wo
 
         nm = _Names(f"{vt}/resnet50lite/stem")
@@ -421,7 +430,69 @@ class MerlotModel(object):
                 x = gn(y, hh * ww, c3, nm.gn(), f"g{i}out{b % 2}", relu=True, shortcut=shortcut)  # relu(GN(y) + shortcut) (:95-96)
                 h, w, c = hh, ww, c3
                 assert c3 == 4 * f
+        self._stem_tape = tape if save else None
         return x, h, w
+
+    def _hybrid_stem_backward(self, d_out, N):
+        """Gradient of _hybrid_stem: walks the tape backwards.  d_out: bf16 gradient of the stem output.  Parameter gradients are
+        ACCUMULATED into the arena (conv kernels through the weight-standardisation backward, GroupNorm gamma/beta directly);
+        activation gradients meet by tensor identity (a block input feeds the first 1x1 and the shortcut)."""
+        st, bf = self.store, self._bufs
+        tape = self._stem_tape
+        grads = {tape[-1][1]["y"].data_ptr(): d_out}
+        red = bf.get("stem.gn_red", (N * 64,), torch.float32)
+        ctr = [0]
+
+        def D(rows, cols):
+            ctr[0] += 1
+            return bf.get(f"stem.d.{ctr[0]}", (rows, cols), torch.bfloat16)
+
+        def acc(t, g):
+            k = t.data_ptr()
+            if k in grads:
+                ops.add_bf16(grads[k], g, grads[k])
+            else:
+                grads[k] = g
+
+        for kind, r in reversed(tape):
+            dy = grads.pop(r["y"].data_ptr(), None)
+            if dy is None:
+                continue
+            if kind == "gn":
+                dx = D(*r["x"].shape)
+                dsc = D(*r["y"].shape) if r["shortcut"] is not None else None
+                ops.group_norm_bwd(dy, r["x"], r["y"] if r["relu"] else None, r["stats"], st.P(f"{r['scope']}/gamma"), dx, dsc,
+                                   st.G(f"{r['scope']}/gamma"), st.G(f"{r['scope']}/beta"), red, N, r["hw"], r["c"], 32, 1e-4, r["relu"])
+                acc(r["x"], dx)
+                if dsc is not None:
+                    acc(r["shortcut"], dsc)
+            elif kind == "pool":
+                dx = D(*r["x"].shape)
+                ops.avgpool2_same_bwd(dy, N, r["h"], r["w"], r["c"], dx)
+                acc(r["x"], dx)
+            else:  # conv
+                wk = st.P(r["kname"])
+                kp, cout, M = r["kp"], r["cout"], N * r["ho"] * r["wo"]
+                if r["k"] == 1:
+                    a = r["x"]
+                else:
+                    a = bf.get("stem.col", (M, kp), torch.bfloat16)
+                    ops.im2col3x3(r["x"], N, r["h"], r["w"], r["cin"], r["stride"], a, sub_half=r["sub_half"])
+                dws = bf.get("stem.dws", (kp, cout), torch.float32, zero=True)
+                ops.gemm(a, dy, a_mn_major=True, b_mn_major=True, out=dws, atomic=True, M=kp, N=cout, K=M)  # d(standardised kernel)
+                ops.ws_weights_bwd(dws, wk, st.G(r["kname"]))
+                if r["sub_half"]:
+                    continue  # the image itself needs no gradient
+                wstd = ops.ws_weights(wk, kp)
+                if r["k"] == 1:
+                    dx = D(M, kp)
+                    ops.gemm(dy, wstd, out=dx)  # dx[M, cin] = dy[M, cout] . wstd[cin, cout]^T
+                else:
+                    dcol = bf.get("stem.dcol", (M, kp), torch.bfloat16)
+                    ops.gemm(dy, wstd, out=dcol)
+                    dx = D(N * r["h"] * r["w"], r["cin"])
+                    ops.col2im3x3(dcol, N, r["h"], r["w"], r["cin"], r["stride"], dx)
+                acc(r["x"], dx)
 
     def _side_stream(self):
         """Stream for the language-only stack (set MERLOT_NO_SIDE_STREAM=1 to serialise everything on one stream)."""
@@ -869,10 +940,11 @@ class MerlotModel(object):
         -> ViT."""
         if not self._save:
             raise RuntimeError("MerlotModel was built without save_for_backward (is_training=False)")
-        if self._resnet_layers:
+        if self._resnet_layers and os.environ.get("MERLOT_STEM_BACKWARD", "0") != "1":
             raise NotImplementedError(
                 "training through the hybrid ResNet-lite stem (resnet_layers={}) is not provided yet: its forward runs (inference / "
-                "zero-shot configs), its backward does not; use config.patch_embed_variant() to train".format(self._resnet_layers))
+                "zero-shot configs); its backward is written but has not been verified on hardware (set MERLOT_STEM_BACKWARD=1 to "
+                "run it); use config.patch_embed_variant() to train".format(self._resnet_layers))
         cfg, st, bf, D = self.config, self.store, self._bufs, self._dims
         H, B, Lj, N = self.hidden_size, self.B, self.L, D["N"]
         Sj, Pz, vcl, Sv, Mv, np_, ncls = D["Sj"], D["Pz"], D["vcl"], D["Sv"], D["Mv"], D["np"], D["ncls"]
@@ -935,9 +1007,19 @@ class MerlotModel(object):
         ops.group_rowsum(dxv, N, Sv, ncls, np_, self._grid_idxmap(D["h1"], D["w1"]), st.G(f"{vt}/pos_embs/pos_embs"), H)
         dpatch = bf.get("bwd.dpatch", (N * np_, H), torch.bfloat16)
         ops.vit_assemble_bwd(dxv, dpatch, N, np_, ncls, H)
-        ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
-        ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
-                 out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
+        if not self._resnet_layers:
+            ops.bias_grad(dpatch, st.G(f"{vt}/conv2d/bias"), rows=N * np_, N=H)
+            ops.gemm(bf.get("vit.A", (N * np_, D["Kp"]), torch.bfloat16), dpatch, a_mn_major=True, b_mn_major=True,
+                     out=st.G(f"{vt}/conv2d/kernel"), atomic=True, M=D["Kp"], N=H, K=N * np_)
+        else:  # conv_postresnet_proj (1x1 + bias, not standardised), then the stem's tape
+            rc = self._stem_tape[-1][1]["y"]
+            Cr = rc.shape[1]
+            ops.bias_grad(dpatch, st.G(f"{vt}/conv_postresnet_proj/bias"), rows=N * np_, N=H)
+            ops.gemm(rc, dpatch, a_mn_major=True, b_mn_major=True, out=st.G(f"{vt}/conv_postresnet_proj/kernel"), atomic=True,
+                     M=Cr, N=H, K=N * np_)
+            d_rc = bf.get("bwd.d_rc", (N * np_, Cr), torch.bfloat16)
+            ops.gemm(dpatch, st.W(f"{vt}/conv_postresnet_proj/kernel"), out=d_rc)  # [M, H] . [Cr, H]^T
+            self._hybrid_stem_backward(d_rc, N)
     def _embed_bwd(self, tag, norm_scope_name, ids_2d, dy, remap, dropout, groups, Lseq):
         st, bf = self.store, self._bufs
         H, R = self.hidden_size, ids_2d.numel()

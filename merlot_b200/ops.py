@@ -298,6 +298,32 @@ def avgpool2_same(x, N, h, w, Cc, y):
     L.check(L.lib().merlot_avgpool2_same(C.c_void_p(x.data_ptr()), N, h, w, Cc, C.c_void_p(y.data_ptr()), _stream()))
 
 
+def group_norm_bwd(dy, x, y, stats, gamma, dx, dshortcut, dgamma, dbeta, red, N, HW, Cc, groups=32, eps=1e-4, relu=True):
+    L.check(L.lib().merlot_group_norm_bwd(C.c_void_p(dy.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(_ptr(y)),
+                                          C.c_void_p(stats.data_ptr()), C.c_void_p(gamma.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                          C.c_void_p(_ptr(dshortcut)), C.c_void_p(dgamma.data_ptr()), C.c_void_p(dbeta.data_ptr()),
+                                          C.c_void_p(red.data_ptr()), N, HW, Cc, groups, C.c_float(eps), int(relu), _stream()))
+
+
+def avgpool2_same_bwd(dy, N, h, w, Cc, dx):
+    L.check(L.lib().merlot_avgpool2_same_bwd(C.c_void_p(dy.data_ptr()), N, h, w, Cc, C.c_void_p(dx.data_ptr()), _stream()))
+
+
+def col2im3x3(dcol, N, h, w, Cin, stride, dx):
+    L.check(L.lib().merlot_col2im3x3(C.c_void_p(dcol.data_ptr()), N, h, w, Cin, stride, dcol.stride(0), C.c_void_p(dx.data_ptr()), _stream()))
+
+
+def ws_weights_bwd(dws, w2d, dw2d):
+    rows, cout = w2d.shape
+    L.check(L.lib().merlot_ws_weights_bwd(C.c_void_p(dws.data_ptr()), dws.stride(0), C.c_void_p(w2d.data_ptr()), rows, cout,
+                                          C.c_void_p(dw2d.data_ptr()), _stream()))
+
+
+def add_bf16(a, b, out):
+    L.check(L.lib().merlot_add_bf16(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+                                    C.c_longlong(a.numel()), _stream()))
+
+
 def vit_assemble_fwd(patch, pos_table, cls_emb, xsum, N, h1, w1, ncls, H):
     L.check(L.lib().merlot_vit_assemble_fwd(C.c_void_p(patch.data_ptr()), C.c_void_p(pos_table.data_ptr()),
                                             C.c_void_p(cls_emb.data_ptr()), C.c_void_p(xsum.data_ptr()), N, h1, w1, ncls, 64, H,

@@ -117,3 +117,114 @@ def test_hybrid_stem_and_model_forward(tiny_cfg):
     mt.mask_loss()
     with pytest.raises(NotImplementedError, match="hybrid ResNet-lite stem"):
         mt.backward()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward of the stem.  The orchestration and the closed-form gradients are proven on CPU (tools/stem_cpu_emulation.py:
+# 54 parameter gradients within 2.4e-6 of autograd); the CUDA kernels below were written when the round's GPU budget was
+# spent, so they stay behind MERLOT_STEM_BACKWARD=1 (same switch as the host path) until a GPU run has confirmed them.
+# ---------------------------------------------------------------------------------------------------------------
+import os
+
+bwd = pytest.mark.skipif(os.environ.get("MERLOT_STEM_BACKWARD", "0") != "1", reason="stem backward kernels not yet verified on hardware")
+
+
+@bwd
+@pytest.mark.parametrize("N,HW,C,relu,short", [(2, 35, 32, True, False), (3, 63, 64, False, False), (2, 24, 256, True, True), (1, 7, 1024, True, True)])
+def test_group_norm_backward(ops, N, HW, C, relu, short):
+    g = torch.Generator().manual_seed(C + HW)
+    x = (torch.randn(N, HW, 1, C, generator=g) * 1.5 + 0.3).bfloat16()
+    sc = torch.randn(N, HW, 1, C, generator=g).bfloat16() if short else None
+    dy = (torch.randn(N, HW, 1, C, generator=g) * 0.2).bfloat16()
+    gam, bet = torch.randn(C, generator=g) * 0.3 + 1.0, torch.randn(C, generator=g) * 0.2
+    xr, gr, br = x.float().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    scr = sc.float().requires_grad_(True) if short else None
+    ref = O.group_norm(xr, {"s/gamma": gr, "s/beta": br}, "s")
+    if short:
+        ref = ref + scr
+    if relu:
+        ref = torch.relu(ref)
+    (ref * dy.float()).sum().backward()
+    dev = lambda t: t.reshape(N * HW, C).to(DEV)
+    y = torch.empty(N * HW, C, dtype=torch.bfloat16, device=DEV)
+    stats, red = torch.empty(N * 64, device=DEV), torch.empty(N * 64, device=DEV)
+    ops.group_norm_fwd(dev(x), gam.to(DEV), bet.to(DEV), y, stats, N, HW, C, 32, 1e-4, relu, dev(sc) if short else None)
+    dx = torch.empty_like(y)
+    dsc = torch.empty_like(y) if short else None
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ops.group_norm_bwd(dev(dy), dev(x), y if relu else None, stats, gam.to(DEV), dx, dsc, dg, db, red, N, HW, C, 32, 1e-4, relu)
+    assert rel(dx, xr.grad.reshape(N * HW, C)) < 1.5e-2
+    assert rel(dg, gr.grad) < 1.5e-2 and rel(db, br.grad) < 1.5e-2
+    if short:
+        assert rel(dsc, scr.grad.reshape(N * HW, C)) < 1.5e-2
+
+
+@bwd
+def test_pool_col2im_ws_backward(ops):
+    g = torch.Generator().manual_seed(7)
+    for N, h, w, C in ((2, 9, 7, 32), (1, 12, 22, 64)):  # avg-pool: adjoint of the forward (ragged windows weigh 1/cnt)
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+        x = torch.randn(N, h, w, C, generator=g, requires_grad=True)
+        dy = torch.randn(N, ho, wo, C, generator=g).bfloat16()
+        (O.avg_pool_same(x, 2) * dy.float()).sum().backward()
+        dx = torch.empty(N * h * w, C, dtype=torch.bfloat16, device=DEV)
+        ops.avgpool2_same_bwd(dy.reshape(-1, C).to(DEV), N, h, w, C, dx)
+        assert rel(dx, x.grad.reshape(N * h * w, C)) < 4e-3
+    for N, h, w, C, stride in ((2, 9, 7, 32, 1), (1, 8, 12, 64, 1), (2, 10, 14, 32, 2)):  # col2im = im2col^T
+        ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
+        dcol = torch.randn(N * ho * wo, 9 * C, generator=g).bfloat16()
+        x = torch.randn(N, h, w, C, generator=g).bfloat16()
+        col = torch.empty(N * ho * wo, 9 * C, dtype=torch.bfloat16, device=DEV)
+        ops.im2col3x3(x.to(DEV), N, h, w, C, stride, col)
+        dx = torch.empty(N * h * w, C, dtype=torch.bfloat16, device=DEV)
+        ops.col2im3x3(dcol.to(DEV), N, h, w, C, stride, dx)
+        lhs = (col.float().cpu() * dcol.float()).sum().item()          # <im2col(x), d>
+        rhs = (x.float().reshape(-1, C) * dx.float().cpu()).sum().item()  # <x, col2im(d)>
+        assert abs(lhs - rhs) <= 2e-2 * max(1.0, abs(lhs))
+    for kh, cin, cout in ((3, 16, 32), (1, 64, 24)):  # weight standardisation backward vs autograd
+        rows = kh * kh * cin
+        w2 = (torch.randn(rows, cout, generator=g) * 0.2 + 0.05).requires_grad_(True)
+        dws = torch.randn(rows, cout, generator=g)
+        mean = w2.mean(0, keepdim=True)
+        ws = (w2 - mean) * torch.rsqrt(((w2 - mean) ** 2).mean(0, keepdim=True) + 1e-5)
+        (ws * dws).sum().backward()
+        dw = torch.full((rows, cout), 0.5, device=DEV)  # accumulates
+        ops.ws_weights_bwd(dws.to(DEV), w2.detach().to(DEV), dw)
+        assert rel(dw - 0.5, w2.grad) < 1e-4
+    a = torch.randn(4096, generator=g).bfloat16()
+    b = torch.randn(4096, generator=g).bfloat16()
+    out = torch.empty(4096, dtype=torch.bfloat16, device=DEV)
+    ops.add_bf16(a.to(DEV), b.to(DEV), out)
+    assert torch.equal(out.cpu(), (a.float() + b.float()).bfloat16())
+
+
+@bwd
+def test_training_step_through_the_stem(tiny_cfg):
+    """Full pretraining losses with the hybrid stem, every parameter gradient (stem included) against oracle autograd."""
+    from merlot_b200.modeling import MerlotModel
+    from tests.test_gpu_model import build, synth
+    cfg = _stem_cfg(tiny_cfg)
+    batch, nc, Lc = 2, 2, 16
+    image, ids, shuf, vid = synth(cfg, batch, nc, Lc, 64, 96, 0)
+    params, store, _ = build(cfg)
+    draws = O.make_mask_draws(2, 32, 6, cfg["vocab_size"], seed=5)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    gm = {"masked_ids": m.lang_mask_info["masked_ids"].cpu().reshape(2, 32), "masked_idx": m.lang_mask_info["masked_idx"].cpu()}
+    om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)
+    m.mask_loss(), m.contrastive_loss(), m.temporal_loss(shuf.to(DEV), vid.to(DEV))
+    total_ref, _ = O.pretrain_losses(om, shuf, vid)
+    store.g.zero_()
+    m.backward()
+    total_ref.backward()
+    grads = store.to_tf_dict("g")
+    worst = {}
+    for k, v in leaf.items():
+        if v.grad is None or float(v.grad.norm()) < 1e-7:
+            continue
+        worst[k] = rel(grads[k], v.grad)
+    stem = {k: r for k, r in worst.items() if "resnet50lite" in k or "conv_postresnet_proj" in k}
+    print("stem gradient parity: worst", max(stem.values()), "median", sorted(stem.values())[len(stem) // 2], "non-stem worst",
+          max(r for k, r in worst.items() if k not in stem))
+    assert len(stem) > 40 and max(stem.values()) < 2e-1 and sorted(stem.values())[len(stem) // 2] < 6e-2
