@@ -155,3 +155,15 @@ def test_process_example_matches_numpy_restatement():
     assert D.num_shuffle_probs(4, 0.4)[:2] == [0.6, 1e-6] and abs(D.expected_out_of_place(4, 0.4) - (1.2 + 1e-6)) < 1e-12
     with pytest.raises(ValueError):
         D.process_example({**feats, "input_ids": feats["input_ids"][:, :7]}, {}, model_cfg)
+
+
+def test_hybrid_stem_orchestration_against_autograd():
+    """tools/stem_cpu_emulation.py: the stem's forward tape and backward walk (merlot_b200/modeling.py) driven with fp32
+    emulations of the K13 / K1 calls must reproduce the oracle's forward and torch-autograd parameter gradients (< 1e-3; it
+    reaches ~2e-6).  Runs in a subprocess because it swaps merlot_b200.ops entry points."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stem_cpu_emulation.py")], cwd=ROOT, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "parameter gradients, worst rel err" in r.stdout
