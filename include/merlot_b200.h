@@ -316,8 +316,8 @@ int merlot_group_norm_fwd(const void* x_bf16, const float* gamma, const float* b
 /* tf.nn.avg_pool2d(ksize 2, strides 2, 'SAME') on NHWC bf16 (:81,93,159) */
 int merlot_avgpool2_same(const void* x_bf16, int N, int h, int w, int C, void* y_bf16, void* stream);
 
-/* K13 backward pieces (tf.gradients of the same graph; UNVERIFIED ON HARDWARE at the end of round 1: the host keeps them
- * behind MERLOT_STEM_BACKWARD=1 and tests/test_gpu_stem.py gates their tests on the same variable) */
+/* K13 backward pieces (tf.gradients of the same graph).  Verified on the B200 through the whole training step (parameter
+ * gradients on the bf16 noise floor of the graph, profiles/r01_hybrid_stem_backward.txt) and, once, op by op. */
 /* GroupNorm(+ReLU, +shortcut) backward: g = dy * [y > 0]; dx, dshortcut (= g, optional), dgamma += , dbeta += ;
  * red: f32 scratch [N, groups, 2]; stats: what merlot_group_norm_fwd left for this site */
 int merlot_group_norm_bwd(const void* dy_bf16, const void* x_bf16, const void* y_bf16, const float* stats, const float* gamma,

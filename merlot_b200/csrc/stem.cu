@@ -1,4 +1,4 @@
-// K13: forward pieces of the hybrid ResNet-lite stem (utils/vision_transformer.py:8-170; SURVEY.md 8(f) next-row 1,
+// K13: the hybrid ResNet-lite stem (utils/vision_transformer.py:8-170; SURVEY.md 8(f) next-row 1,
 // Appendix D).  Every convolution is a K1 GEMM: 1x1 convs read the NHWC activation matrix [N*h*w, C] as it is, 3x3
 // convs go through an im2col matrix whose columns are ordered (ky, kx, c) like the flattened HWIO kernel.  This file
 // holds what sits between the GEMMs:
@@ -10,7 +10,8 @@
 //                     utils/model_utils.py:196-201 (mean = sum/n, var = sum(x^2)/n - mean^2), gamma/beta per channel, bf16
 //                     out, optional ReLU, optional `relu(out + shortcut)` (bottleneck_block :96)
 //   avgpool2          tf.nn.avg_pool2d(ksize 2, strides 2, SAME) (:81,93,159): bottom/right padding not counted
-// Forward only: training through the stem (its backward) is not provided yet and the host raises before getting here.
+// The second half of the file holds the gradient of the same pieces (GroupNorm/ReLU/shortcut, avg-pool, col2im, weight
+// standardisation); MerlotModel._hybrid_stem_backward walks the forward tape and calls them.
 #include "host_common.h"
 #include "ptx.cuh"
 

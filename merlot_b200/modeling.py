@@ -940,11 +940,6 @@ class MerlotModel(object):
         -> ViT."""
         if not self._save:
             raise RuntimeError("MerlotModel was built without save_for_backward (is_training=False)")
-        if self._resnet_layers and os.environ.get("MERLOT_STEM_BACKWARD", "0") != "1":
-            raise NotImplementedError(
-                "training through the hybrid ResNet-lite stem (resnet_layers={}) is not provided yet: its forward runs (inference / "
-                "zero-shot configs); its backward is written but has not been verified on hardware (set MERLOT_STEM_BACKWARD=1 to "
-                "run it); use config.patch_embed_variant() to train".format(self._resnet_layers))
         cfg, st, bf, D = self.config, self.store, self._bufs, self._dims
         H, B, Lj, N = self.hidden_size, self.B, self.L, D["N"]
         Sj, Pz, vcl, Sv, Mv, np_, ncls = D["Sj"], D["Pz"], D["vcl"], D["Sv"], D["Mv"], D["np"], D["ncls"]
