@@ -167,3 +167,47 @@ def test_hybrid_stem_orchestration_against_autograd():
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "parameter gradients, worst rel err" in r.stdout
+
+
+def test_sort_story_scoring_matches_loop_restatement():
+    """downstream/sort_story/score_permutations.py:15-71 restated with explicit loops (as the reference writes it) vs the
+    vectorised merlot_b200.sort_story; closed-form metric values."""
+    import itertools
+    import numpy as np
+    from scipy import stats
+    from merlot_b200 import sort_story as S
+    rng = np.random.default_rng(0)
+    for n in (3, 5):
+        for _ in range(4):
+            p = rng.dirichlet(np.ones(3), size=(n, n))
+            best, best_score = None, -np.inf
+            for perm in itertools.permutations(range(n)):
+                eq, gtlt = np.ones((n, n)), np.ones((n, n))
+                for i in range(n):
+                    for j, pj in enumerate(perm):
+                        if i == pj:
+                            eq[i, j] = p[i, j, 0]
+                        elif i < pj:
+                            gtlt[i, j] = p[i, j, 1]
+                        else:
+                            gtlt[i, j] = p[i, j, 2]
+                sc = np.log(eq).sum() + np.log(gtlt).sum()
+                if sc > best_score:  # strict: the first maximum in itertools order, like the reference's stable sort
+                    best, best_score = perm, sc
+            got, got_score = S.best_permutation(p)
+            assert got == best and abs(got_score - best_score) < 1e-9
+    n = 5  # a model that is certain of the true order recovers it; the reversed story gets the reversed permutation
+    sure = np.full((n, n, 3), 1e-6)
+    for i in range(n):
+        for j in range(n):
+            sure[i, j, 0 if i == j else (1 if i < j else 2)] = 1.0
+    assert S.best_permutation(sure)[0] == (0, 1, 2, 3, 4)
+    assert S.best_permutation(sure[:, ::-1])[0] == (4, 3, 2, 1, 0)
+    assert S.pairwise_acc([0, 1, 2, 3, 4]) == 1.0 and S.pairwise_acc([4, 3, 2, 1, 0]) == 0.0 and S.pairwise_acc([1, 0, 2, 3, 4]) == 0.9
+    assert S.absolute_distance([4, 3, 2, 1, 0]) == 2.4 and S.absolute_distance([0, 1, 2, 3, 4]) == 0.0
+    for story in ([0, 1, 2, 3, 4], [4, 3, 2, 1, 0], [1, 0, 2, 4, 3], [2, 0, 1, 4, 3]):
+        assert abs(S.spearman_acc(story) - stats.spearmanr(story, [0, 1, 2, 3, 4])[0]) < 1e-12
+    ev = S.evaluate([sure, sure[:, ::-1]])
+    assert ev["stories"] == [(0, 1, 2, 3, 4), (4, 3, 2, 1, 0)] and ev["pairwise"] == 0.5 and abs(ev["spearman"]) < 1e-12
+    with pytest.raises(ValueError):
+        S.permutation_scores(np.ones((5, 4, 3)))
