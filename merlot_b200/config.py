@@ -68,7 +68,8 @@ class NeatConfig(object):
 def patch_embed_variant(model_config: dict) -> dict:
     """Return a copy of a `model:` section with the hybrid ResNet stem switched off (resnet_layers: []), i.e. the
     16x16 patch-embed path of utils/vision_transformer.py:194-205 that BASELINE.json's north star names.
-    merlot.yaml as shipped selects the hybrid stem (SURVEY.md discrepancy 1), which this build raises on."""
+    merlot.yaml as shipped selects the hybrid stem (SURVEY.md discrepancy 1); that path (K13, csrc/stem.cu) runs forward and
+    backward as well -- this switch only names the variant the headline benchmark measures."""
     c = deepcopy(model_config)
     c["resnet_layers"] = []
     return c

@@ -119,7 +119,7 @@ class _Stack:
 
     def backward(self, dy, dh_in):
         d = self.d
-        scratch = self.bufs.get("stack.scratch", (L.lib().merlot_stack_scratch_bytes(C.byref(d)),), torch.uint8)
+        scratch = self.bufs.get(f"{self.tag}.scratch", (L.lib().merlot_stack_scratch_bytes(C.byref(d)),), torch.uint8)
         d.dy, d.dh_in, d.scratch = dy.data_ptr(), dh_in.data_ptr(), scratch.data_ptr()
         L.check(L.lib().merlot_stack_backward(C.byref(d), ops._stream()))
         return dh_in
@@ -439,6 +439,7 @@ class MerlotModel(object):
         activation gradients meet by tensor identity (a block input feeds the first 1x1 and the shortcut)."""
         st, bf = self.store, self._bufs
         tape = self._stem_tape
+        trace = getattr(self, "_stem_trace", None)  # tests set this to a list: every op's (dy, dx, d_shortcut) is recorded
         grads = {tape[-1][1]["y"].data_ptr(): d_out}
         red = bf.get("stem.gn_red", (N * 64,), torch.float32)
         ctr = [0]
@@ -463,12 +464,16 @@ class MerlotModel(object):
                 dsc = D(*r["y"].shape) if r["shortcut"] is not None else None
                 ops.group_norm_bwd(dy, r["x"], r["y"] if r["relu"] else None, r["stats"], st.P(f"{r['scope']}/gamma"), dx, dsc,
                                    st.G(f"{r['scope']}/gamma"), st.G(f"{r['scope']}/beta"), red, N, r["hw"], r["c"], 32, 1e-4, r["relu"])
+                if trace is not None:
+                    trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=dx.clone(), dsc=None if dsc is None else dsc.clone()))
                 acc(r["x"], dx)
                 if dsc is not None:
                     acc(r["shortcut"], dsc)
             elif kind == "pool":
                 dx = D(*r["x"].shape)
                 ops.avgpool2_same_bwd(dy, N, r["h"], r["w"], r["c"], dx)
+                if trace is not None:
+                    trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=dx.clone()))
                 acc(r["x"], dx)
             else:  # conv
                 wk = st.P(r["kname"])
@@ -482,6 +487,8 @@ class MerlotModel(object):
                 ops.gemm(a, dy, a_mn_major=True, b_mn_major=True, out=dws, atomic=True, M=kp, N=cout, K=M)  # d(standardised kernel)
                 ops.ws_weights_bwd(dws, wk, st.G(r["kname"]))
                 if r["sub_half"]:
+                    if trace is not None:
+                        trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=None))
                     continue  # the image itself needs no gradient
                 wstd = ops.ws_weights(wk, kp)
                 if r["k"] == 1:
@@ -492,6 +499,8 @@ class MerlotModel(object):
                     ops.gemm(dy, wstd, out=dcol)
                     dx = D(N * r["h"] * r["w"], r["cin"])
                     ops.col2im3x3(dcol, N, r["h"], r["w"], r["cin"], r["stride"], dx)
+                if trace is not None:
+                    trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=dx.clone()))
                 acc(r["x"], dx)
 
     def _side_stream(self):

@@ -172,7 +172,9 @@ _ln_ws = {}
 
 
 def _ln_workspace(H: int, device) -> torch.Tensor:
-    key = (H, str(device))
+    # one workspace PER STREAM: ln_bwd writes per-block partials and a second launch reads them back, so two streams that
+    # run LayerNorm backwards concurrently (language-only vs joint encoder) must never share the buffer
+    key = (H, str(device), int(torch.cuda.current_stream(device).cuda_stream))
     if key not in _ln_ws:
         _ln_ws[key] = torch.empty(L.lib().merlot_layernorm_bwd_workspace_bytes(H), dtype=torch.uint8, device=device)
     return _ln_ws[key]

@@ -41,6 +41,26 @@ class AdamOptimizer:
         self.store = store
         self.learning_rate = learning_rate
         self.num_train_steps, self.num_warmup_steps = num_train_steps, num_warmup_steps
+        # The arena's hyper-parameter groups were fixed when the ParamStore was built; they must be the ones THIS optimizer
+        # config implies (utils/optimization.py:125-156), otherwise the update would silently use other rates (e.g. a store
+        # built without optimizer_cfg has learning_rate 0 everywhere and would train nothing).
+        from .params import hyper_for
+        ocfg = dict(kwargs, learning_rate=learning_rate)
+        for e in store.entries.values():
+            want = {hyper_for(t, ocfg) for t in e.tf_names}
+            if want != {tuple(e.hyper)}:
+                raise ValueError(f"ParamStore was grouped with other optimizer hyper-parameters than this config gives for "
+                                 f"{e.name}: store {tuple(e.hyper)} vs config {sorted(want)}; build ParamStore(cfg, optimizer_cfg=...)")
+        if all(h[0] == 0 for h, _, _ in store.groups):
+            raise ValueError("every parameter group has learning_rate 0: nothing would be trained")
+        self._frozen = [(off, off + cnt) for h, off, cnt in store.groups if h[0] == 0]
+
+    def zero_frozen_grads(self):
+        """Variables with learning_rate 0 are removed from tvars before tf.gradients / clipping in the reference
+        (utils/optimization.py:149-156): their accumulated gradients are discarded here so they neither enter the global norm
+        nor grow step after step."""
+        for a, b in self._frozen:
+            self.store.g[a:b].zero_()
 
     def scalars(self, hyper, step):
         lr, wd, b1, b2, eps = hyper
@@ -60,6 +80,8 @@ class AdamOptimizer:
         pass advance=False for all but the last partial call of a step."""
         st = self.store
         step = st.global_step
+        if zero_grad:
+            self.zero_frozen_grads()
         skip_ranges = sorted((st.entries[n].offset, st.entries[n].offset + st.entries[n].padded) for n in skip)
         if only is not None:  # complement of `only` is skipped in this call
             cur, extra = 0, []
@@ -101,6 +123,7 @@ class AdamOptimizer:
         if self.clip_norm <= 0.0:
             return None
         st = self.store
+        self.zero_frozen_grads()
         if not hasattr(st, "_clip_scratch"):
             st._clip_scratch = torch.zeros(1, dtype=torch.float64, device=st.device)
             st._clip_norm = torch.zeros(1, dtype=torch.float32, device=st.device)

@@ -180,8 +180,8 @@ class ParamStore:
     """Flat arenas + named views.  `optimizer_cfg` fixes the hyper-parameter grouping (needed only for training)."""
 
     def __init__(self, model_cfg: dict, device="cuda", optimizer_cfg: Optional[dict] = None, with_optimizer_state=True):
-        # resnet_layers != [] selects the hybrid ResNet-lite stem (utils/vision_transformer.py:206-223): its FORWARD is provided
-        # (inference / zero-shot configs); MerlotModel raises NotImplementedError when asked to train through it.
+        # resnet_layers != [] selects the hybrid ResNet-lite stem (utils/vision_transformer.py:206-223); forward and backward
+        # are provided (K13), its variables follow the reference's creation order (stem_variables).
         self.cfg = model_cfg
         self.device = torch.device(device)
         ents = _entries(model_cfg)

@@ -105,8 +105,11 @@ class StepSpec:
 
 
 def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, dist: Optional[DataParallel] = None,
-                     device="cuda"):
-    """model/modeling.py:671-810."""
+                     device="cuda", seed: int = 0, log_attention_probs: bool = True):
+    """model/modeling.py:671-810.  `seed` is the run seed of every random draw of the step (dropout masks, Gumbel noise,
+    span lengths, 10/80/10 options, replacement ids): replica r at step t uses seed + t*world + r, so replicas draw
+    independently like the reference's per-core tf.random ops and two runs with different seeds differ.
+    `log_attention_probs` defaults to the reference's model_fn (modeling.py:691-709 computes attn/* every step)."""
     if store is None:
         store = ParamStore(config.model, device=device, optimizer_cfg=config.optimizer)
         store.init_reference(seed=0)
@@ -121,7 +124,8 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
         model = MerlotModel(config=config.model, is_training=True,  # the reference hard-codes True (:693)
                             image=imgs, input_ids=features["input_ids"], use_tpu=config.device.get("use_tpu", False),
                             shuffled_idx_img=features.get("shuffled_idx_img", None), mask_input=True, params=store,
-                            dropout_seed=store.global_step, dist=dist, log_attention_probs=False)
+                            dropout_seed=seed + store.global_step * (dist.world if dist is not None else 1) +
+                            (dist.rank if dist is not None else 0), dist=dist, log_attention_probs=log_attention_probs)
         lang_loss, lang_losses = model.mask_loss()
         contr_loss, contr_losses = model.contrastive_loss()
         skip = []
@@ -136,6 +140,8 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
         losses.update({f"contr/{k}": v for k, v in contr_losses.items()})
         losses.update({f"temporal/{k}": v for k, v in temp_losses.items()})
         losses["learning_rate"] = optimizer.current_lr()
+        if log_attention_probs:  # modeling.py:709  losses.update(model.attention_log)
+            losses.update({f"attn/{k}": v for k, v in model.attention_log.items()})
 
         def train_op():
             world = dist.world if dist is not None else 1

@@ -141,8 +141,7 @@ def transformer(hidden, mask, p: Params, scope: str, num_layers: int, heads: int
 
 # ------------------------------------------------------------------------------------------------------------
 # Hybrid ResNet-lite stem (utils/vision_transformer.py:8-170) -- SURVEY.md 8(f) next-row 1 / Appendix D.
-# Restated ahead of the CUDA path so that path starts with a checker; merlot_b200 still raises NotImplementedError
-# for resnet_layers != [].
+# The checker of the CUDA stem (K13, merlot_b200/csrc/stem.cu), forward and backward.
 # ------------------------------------------------------------------------------------------------------------
 def _ident(t: torch.Tensor) -> torch.Tensor:
     return t

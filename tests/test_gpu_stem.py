@@ -115,34 +115,32 @@ def test_hybrid_stem_and_model_forward(tiny_cfg):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# backward of the stem.  The orchestration and the closed-form gradients are proven on CPU (tools/stem_cpu_emulation.py:
-# 54 parameter gradients within 2.4e-6 of autograd).  On the B200 the whole training step through the stem lands on the bf16
-# noise floor of the graph (profiles/r01_hybrid_stem_backward.txt).  The three op-level tests ran once on the GPU (GroupNorm
-# without shortcut 1.5e-2, pooling and the col2im adjoint within bf16 rounding); their bars were corrected AFTER that run --
-# relu+shortcut masks flip on near-zero bf16 sums (3-4e-2), the adjoint bar must scale with the vectors' norms -- and could not be
-# re-run inside the round's GPU budget, so they wait behind MERLOT_TEST_STEM_OPS=1; the model-level test below is always on.
+# backward of the stem -- a test design that CAN fail (round-1 review).
+#
+# Why whole-graph bars were useless: a ResNet stem's parameter gradients at random init are sums of random-sign terms; the
+# bf16 graph sits ~4e-2 from fp32 in the FORWARD, which flips ~3 % of the ReLU masks, and a 3 % flip of a random-sign sum is a
+# ~25-30 % relative change of that sum -- on any map size (measured on CPU: the oracle in the reference's bf16 dtype policy vs
+# its fp32 self: median 0.31 at 64x96, 128x192 and batch 8 alike).  So a comparison across DIFFERENT rounding points cannot
+# tell a right gradient from a subtly wrong one.  The tests below compare at IDENTICAL rounding points instead:
+#   (1) op level: each backward kernel vs autograd of the same op, ReLU masks taken from the kernel's own forward output;
+#   (2) in situ: the real tape of lite_resnet50 at 128x192 (maps 64x96 .. 8x12): for EVERY op the GPU's dx / d_shortcut /
+#       parameter gradient vs autograd of that op on the GPU's own saved input and the GPU's own incoming gradient, plus the
+#       routing identity (an op's incoming gradient = sum of its consumers' dx);
+#   (3) model level: the oracle is given the GPU's stem OUTPUT as a leaf: every non-stem gradient and d(stem output) at the
+#       same 4e-2 bar as the patch-embed model test.  (1)+(2)+(3) chain to the whole gradient; tools/stem_cpu_emulation.py
+#       (CPU suite) proves the tape walk in fp32 to 2.4e-6.
 # ---------------------------------------------------------------------------------------------------------------
-import os
-
-bwd = pytest.mark.skipif(os.environ.get("MERLOT_TEST_STEM_OPS", "0") != "1", reason="op-level stem backward bars re-calibrated after the last GPU run")
+OP_BAR = 2e-2   # bf16 rounding of dx (4e-3) + bf16 operands; a wrong term in a backward formula shows up at >= 1e-1
 
 
-@bwd
-@pytest.mark.parametrize("N,HW,C,relu,short", [(2, 35, 32, True, False), (3, 63, 64, False, False), (2, 24, 256, True, True), (1, 7, 1024, True, True)])
+@pytest.mark.parametrize("N,HW,C,relu,short", [(2, 35, 32, True, False), (3, 63, 64, False, False), (2, 24, 256, True, True), (1, 7, 1024, True, True),
+                                               (2, 96, 1024, True, True)])
 def test_group_norm_backward(ops, N, HW, C, relu, short):
     g = torch.Generator().manual_seed(C + HW)
     x = (torch.randn(N, HW, 1, C, generator=g) * 1.5 + 0.3).bfloat16()
     sc = torch.randn(N, HW, 1, C, generator=g).bfloat16() if short else None
     dy = (torch.randn(N, HW, 1, C, generator=g) * 0.2).bfloat16()
     gam, bet = torch.randn(C, generator=g) * 0.3 + 1.0, torch.randn(C, generator=g) * 0.2
-    xr, gr, br = x.float().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
-    scr = sc.float().requires_grad_(True) if short else None
-    ref = O.group_norm(xr, {"s/gamma": gr, "s/beta": br}, "s")
-    if short:
-        ref = ref + scr
-    if relu:
-        ref = torch.relu(ref)
-    (ref * dy.float()).sum().backward()
     dev = lambda t: t.reshape(N * HW, C).to(DEV)
     y = torch.empty(N * HW, C, dtype=torch.bfloat16, device=DEV)
     stats, red = torch.empty(N * 64, device=DEV), torch.empty(N * 64, device=DEV)
@@ -151,14 +149,21 @@ def test_group_norm_backward(ops, N, HW, C, relu, short):
     dsc = torch.empty_like(y) if short else None
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     ops.group_norm_bwd(dev(dy), dev(x), y if relu else None, stats, gam.to(DEV), dx, dsc, dg, db, red, N, HW, C, 32, 1e-4, relu)
-    bar = 6e-2 if short else 1.5e-2  # relu(bf16(GN) + shortcut): masks of near-zero sums flip against the fp32 reference
-    assert rel(dx, xr.grad.reshape(N * HW, C)) < bar
-    assert rel(dg, gr.grad) < bar and rel(db, br.grad) < bar
+    # reference: autograd of the same op with the ReLU mask of the kernel's own forward output (identical rounding points)
+    xr, gr, br = x.float().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    scr = sc.float().requires_grad_(True) if short else None
+    ref = O.group_norm(xr, {"s/gamma": gr, "s/beta": br}, "s")
     if short:
-        assert rel(dsc, scr.grad.reshape(N * HW, C)) < bar
+        ref = ref + scr
+    if relu:
+        ref = ref * (y.float().cpu().reshape(N, HW, 1, C) > 0).float()
+    (ref * dy.float()).sum().backward()
+    assert rel(dx, xr.grad.reshape(N * HW, C)) < OP_BAR
+    assert rel(dg, gr.grad) < OP_BAR and rel(db, br.grad) < OP_BAR
+    if short:
+        assert rel(dsc, scr.grad.reshape(N * HW, C)) < OP_BAR
 
 
-@bwd
 def test_pool_col2im_ws_backward(ops):
     g = torch.Generator().manual_seed(7)
     for N, h, w, C in ((2, 9, 7, 32), (1, 12, 22, 64)):  # avg-pool: adjoint of the forward (ragged windows weigh 1/cnt)
@@ -169,18 +174,18 @@ def test_pool_col2im_ws_backward(ops):
         dx = torch.empty(N * h * w, C, dtype=torch.bfloat16, device=DEV)
         ops.avgpool2_same_bwd(dy.reshape(-1, C).to(DEV), N, h, w, C, dx)
         assert rel(dx, x.grad.reshape(N * h * w, C)) < 4e-3
-    for N, h, w, C, stride in ((2, 9, 7, 32, 1), (1, 8, 12, 64, 1), (2, 10, 14, 32, 2)):  # col2im = im2col^T
+    for N, h, w, C, stride in ((2, 9, 7, 32, 1), (1, 8, 12, 64, 1), (2, 10, 14, 32, 2)):  # col2im = im2col^T, elementwise
         ho, wo = (h + 2 - 3) // stride + 1, (w + 2 - 3) // stride + 1
         dcol = torch.randn(N * ho * wo, 9 * C, generator=g).bfloat16()
-        x = torch.randn(N, h, w, C, generator=g).bfloat16()
-        col = torch.empty(N * ho * wo, 9 * C, dtype=torch.bfloat16, device=DEV)
-        ops.im2col3x3(x.to(DEV), N, h, w, C, stride, col)
         dx = torch.empty(N * h * w, C, dtype=torch.bfloat16, device=DEV)
         ops.col2im3x3(dcol.to(DEV), N, h, w, C, stride, dx)
-        lhs = (col.float().cpu() * dcol.float()).sum().item()          # <im2col(x), d>
-        rhs = (x.float().reshape(-1, C) * dx.float().cpu()).sum().item()  # <x, col2im(d)>
-        scale = (col.float().norm().item() * dcol.float().norm().item()) / (dcol.numel() ** 0.5)  # std of such an inner product
-        assert abs(lhs - rhs) <= 2e-3 * scale  # observed 2.5e-4 * scale: bf16 rounding of dx
+        # reference: the adjoint of the oracle's conv with an identity-like kernel bank = scatter of the 9 taps
+        xr = torch.zeros(N, h + 2, w + 2, C)
+        d4 = dcol.float().reshape(N, ho, wo, 9, C)
+        for t in range(9):
+            ky, kx = t // 3, t % 3
+            xr[:, ky:ky + (ho - 1) * stride + 1:stride, kx:kx + (wo - 1) * stride + 1:stride] += d4[:, :, :, t]
+        assert rel(dx, xr[:, 1:h + 1, 1:w + 1].reshape(N * h * w, C)) < 4e-3  # one bf16 rounding of the 9-tap sum
     for kh, cin, cout in ((3, 16, 32), (1, 64, 24)):  # weight standardisation backward vs autograd
         rows = kh * kh * cin
         w2 = (torch.randn(rows, cout, generator=g) * 0.2 + 0.05).requires_grad_(True)
@@ -198,36 +203,123 @@ def test_pool_col2im_ws_backward(ops):
     assert torch.equal(out.cpu(), (a.float() + b.float()).bfloat16())
 
 
-def test_training_step_through_the_stem(tiny_cfg):
-    """Full pretraining losses with the hybrid stem, every parameter gradient (stem included) against fp32 oracle autograd.
-    The bars are multiples of the graph's own bf16 noise floor: the oracle evaluated with the reference's bf16 dtype policy
-    (lite_resnet50(rnd=bf16_round)) sits at median 0.32 / worst 0.38 from its fp32 self on these 4x6 maps (GroupNorm over 24
-    positions + ReLU masks); the CUDA path measured median 0.26 / worst 0.39 (profiles/r01_hybrid_stem_backward.txt)."""
+def _stem_model(tiny_cfg, h0, w0, batch=2, nc=2, save=True):
     from merlot_b200.modeling import MerlotModel
     from tests.test_gpu_model import build, synth
     cfg = _stem_cfg(tiny_cfg)
-    batch, nc, Lc = 2, 2, 16
-    image, ids, shuf, vid = synth(cfg, batch, nc, Lc, 64, 96, 0)
+    image, ids, shuf, vid = synth(cfg, batch, nc, 16, h0, w0, 0)
     params, store, _ = build(cfg)
-    draws = O.make_mask_draws(2, 32, 6, cfg["vocab_size"], seed=5)
+    draws = O.make_mask_draws(batch, 32, 6, cfg["vocab_size"], seed=5)
     m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
-                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=True)
+                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=save)
+    return cfg, m, params, store, (image, ids, shuf, vid)
+
+
+def test_stem_backward_in_situ(tiny_cfg):
+    """Every op of the real lite_resnet50 tape (128x192 input: maps 64x96, 32x48, 16x24, 8x12; 4 frames), backward vs autograd
+    of that single op on the GPU's own saved input and incoming gradient; plus gradient routing."""
+    cfg, m, params, store, (image, ids, shuf, vid) = _stem_model(tiny_cfg, 128, 192)
+    N = image.shape[0]
+    tape = m._stem_tape
+    rc = tape[-1][1]["y"]
+    g = torch.Generator().manual_seed(3)
+    d_rc = (torch.randn(rc.shape, generator=g) * 0.1).bfloat16().to(DEV)
+    store.g.zero_()
+    m._stem_trace = []
+    m._hybrid_stem_backward(d_rc.clone(), N)
+    trace = m._stem_trace
+    m._stem_trace = None
+    assert len(trace) == len(tape)
+    f = lambda t: t.float().cpu()
+    worst = {"gn": 0.0, "conv": 0.0, "pool": 0.0, "param": 0.0}
+    produced = {}   # y ptr -> list of dx contributions routed to it
+    for t in trace:
+        r, kind = t["r"], t["kind"]
+        dy = f(t["dy"])
+        if t.get("dx") is not None:
+            produced.setdefault(r["x"].data_ptr(), []).append(f(t["dx"]))
+        if t.get("dsc") is not None:
+            produced.setdefault(r["shortcut"].data_ptr(), []).append(f(t["dsc"]))
+        if kind == "gn":
+            hw, c = r["hw"], r["c"]
+            x = f(r["x"]).reshape(N, hw, 1, c).requires_grad_(True)
+            gam = store.P(f"{r['scope']}/gamma").float().cpu().clone().requires_grad_(True)
+            bet = store.P(f"{r['scope']}/beta").float().cpu().clone().requires_grad_(True)
+            out = O.group_norm(x, {"s/gamma": gam, "s/beta": bet}, "s")
+            sc = None
+            if r["shortcut"] is not None:
+                sc = f(r["shortcut"]).reshape(N, hw, 1, c).requires_grad_(True)
+                out = out + sc
+            if r["relu"]:
+                out = out * (f(r["y"]).reshape(N, hw, 1, c) > 0).float()
+            (out * dy.reshape(N, hw, 1, c)).sum().backward()
+            e = [rel(f(t["dx"]), x.grad.reshape(N * hw, c))]
+            if sc is not None:
+                e.append(rel(f(t["dsc"]), sc.grad.reshape(N * hw, c)))
+            worst["gn"] = max(worst["gn"], *e)
+            worst["param"] = max(worst["param"], rel(store.G(f"{r['scope']}/gamma"), gam.grad), rel(store.G(f"{r['scope']}/beta"), bet.grad))
+        elif kind == "pool":
+            x = f(r["x"]).reshape(N, r["h"], r["w"], r["c"]).requires_grad_(True)
+            ho, wo = (r["h"] + 1) // 2, (r["w"] + 1) // 2
+            (O.avg_pool_same(x, 2) * dy.reshape(N, ho, wo, r["c"])).sum().backward()
+            worst["pool"] = max(worst["pool"], rel(f(t["dx"]), x.grad.reshape(-1, r["c"])))
+        else:
+            k, cin, cout = r["k"], r["cin"], r["cout"]
+            x = f(r["x"]).reshape(N, r["h"], r["w"], cin)
+            if r["sub_half"]:
+                x = (x - 0.5).bfloat16().float()
+            x.requires_grad_(True)
+            kern = store.P(r["kname"]).float().cpu().clone().reshape(k, k, cin, cout).requires_grad_(True)
+            out = O.conv2d_fixed_padding(x, kern, strides=r["stride"], weight_standardization=True)
+            (out * dy.reshape(out.shape)).sum().backward()
+            if t["dx"] is not None:
+                worst["conv"] = max(worst["conv"], rel(f(t["dx"]), x.grad.reshape(-1, cin)))
+            worst["param"] = max(worst["param"], rel(store.G(r["kname"]).float().cpu().reshape(k, k, cin, cout), kern.grad))
+    # routing: the gradient each op received = sum of the dx its consumers produced (bf16 adds in between)
+    route = 0.0
+    for t in trace:
+        key = t["r"]["y"].data_ptr()
+        if key in produced:
+            route = max(route, rel(f(t["dy"]), sum(produced[key])))
+    print(f"stem backward in situ ({len(trace)} ops): worst rel err {worst}, routing {route:.2e}")
+    assert worst["gn"] < OP_BAR and worst["conv"] < OP_BAR and worst["pool"] < 5e-3 and worst["param"] < OP_BAR, worst
+    assert route < 8e-3  # one or two bf16 roundings of the sum
+    store.g.zero_()
+
+
+def test_training_step_through_the_stem(tiny_cfg, monkeypatch):
+    """Whole pretraining step with the hybrid stem; the oracle's lite_resnet50 is replaced by a LEAF holding the GPU's stem
+    output, so the two graphs share their rounding points at the stem boundary: the three losses, every non-stem gradient and the
+    gradient handed to the stem are compared at the bars of the patch-embed model test (1e-3 losses, 4e-2 gradients)."""
+    cfg, m, params, store, (image, ids, shuf, vid) = _stem_model(tiny_cfg, 128, 192)
+    N = image.shape[0]
+    rc = m._stem_tape[-1][1]["y"]
+    hs, ws = 128 // 16, 192 // 16
+    leaf_rc = rc.float().cpu().reshape(N, hs, ws, rc.shape[1]).clone().requires_grad_(True)
+    monkeypatch.setattr(O, "lite_resnet50", lambda x, p, scope, layers, width=64, rnd=O._ident: leaf_rc)
     leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     gm = {"masked_ids": m.lang_mask_info["masked_ids"].cpu().reshape(2, 32), "masked_idx": m.lang_mask_info["masked_idx"].cpu()}
     om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)
-    m.mask_loss(), m.contrastive_loss(), m.temporal_loss(shuf.to(DEV), vid.to(DEV))
+    ll, _ = m.mask_loss()
+    cl, _ = m.contrastive_loss()
+    tl, _ = m.temporal_loss(shuf.to(DEV), vid.to(DEV))
     total_ref, _ = O.pretrain_losses(om, shuf, vid)
+    total = float(ll) + float(cl) + float(tl)
+    assert abs(total - float(total_ref)) <= 1e-3 * abs(float(total_ref)), (total, float(total_ref))
     store.g.zero_()
     m.backward()
     total_ref.backward()
     grads = store.to_tf_dict("g")
     worst = {}
     for k, v in leaf.items():
-        if v.grad is None or float(v.grad.norm()) < 1e-7:
+        if "resnet50lite" in k or v.grad is None or float(v.grad.norm()) < 1e-7:
             continue
         worst[k] = rel(grads[k], v.grad)
-    stem = {k: r for k, r in worst.items() if "resnet50lite" in k or "conv_postresnet_proj" in k}
-    print("stem gradient parity: worst", max(stem.values()), "median", sorted(stem.values())[len(stem) // 2], "non-stem worst",
-          max(r for k, r in worst.items() if k not in stem))
-    assert len(stem) > 40 and max(stem.values()) < 0.6 and sorted(stem.values())[len(stem) // 2] < 0.45
-    assert max(r for k, r in worst.items() if k not in stem) < 0.12  # the rest of the model sees the stem's noise upstream (measured 0.071)
+    d_rc = m._bufs.get("bwd.d_rc", (N * hs * ws, rc.shape[1]), torch.bfloat16)
+    e_rc = rel(d_rc, leaf_rc.grad.reshape(N * hs * ws, -1))
+    stem_norm = sum(float(grads[k].norm()) for k in grads if "resnet50lite" in k)
+    print(f"stem boundary: d(stem out) rel {e_rc:.3e}; non-stem worst {max(worst.values()):.3e}; stem grad norm sum {stem_norm:.3e}")
+    assert max(worst.values()) < 4e-2, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    assert e_rc < 4e-2
+    assert stem_norm > 0 and all(torch.isfinite(grads[k]).all() for k in grads)
+    store.g.zero_()
