@@ -356,6 +356,110 @@ def run_ours(args):
         dist.barrier()
 
 
+def run_other_config(args):
+    """`--config 1|4|5`: the other BASELINE.json configs as single-GPU (or per-rank) timed loops -- parity-test shapes, reported
+    beside the headline, never instead of it.  1: MerlotModel forward, 1 frame 192x320 + 32 tokens, batch 1 (2-D ids);
+    4: sort_story zero-shot forward, 32 rows x 5 frames 384x384 + all-pairs temporal softmax
+    (downstream/sort_story/get_zero_shot_logits.py:55-90); 5: stress pretrain step, 8 segments x 384-token captions, batch 16
+    per GPU, joint sequence 3608 (needs max_position_embeddings >= 3072: stated override, utils/model_utils.py:282)."""
+    from merlot_b200 import _lib as L
+    from merlot_b200.modeling import MerlotModel
+    from merlot_b200.train import DataParallel, model_fn_builder, synthetic_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = DataParallel("nccl") if world > 1 else None
+    config = load_config()
+    m = config.model
+    g = torch.Generator().manual_seed(rank)
+    sustained, _, _, how = peaks()
+    if args.config == 5:
+        m.update(num_chunks_in_group=8, max_position_embeddings=3072)
+        config.data.update(num_chunks=8, chunk_text_len=384)
+        batch = args.batch or 16
+        model_fn = model_fn_builder(config, dist=dist, device=dev)
+        feats = synthetic_batch(config, batch, seed=rank, device=dev, num_chunks=8, chunk_text_len=384)
+        segs = batch * 8
+        flops_step = 115.0e12 * batch / 16  # SURVEY 8(d): 38.33 TFLOP fwd, x3 per step at batch 16
+
+        def step():
+            spec = model_fn(feats, None, "train", None)
+            spec.train_op()
+        what = ("configs[4] stress: 8 segments x 384-token captions, 192x352 frames, joint sequence 3608, pretrain step "
+                "fwd+bwd+AdamW, hidden dropout 0.1; max_position_embeddings overridden 1024 -> 3072")
+        metric = METRIC
+    else:
+        from merlot_b200.params import ParamStore
+        m["hidden_dropout_prob"] = 0.0
+        if args.config == 4:
+            m.update(num_chunks_in_group=5, image_size=[384, 384])
+            batch, n, hw = args.batch or 32, 5, (384, 384)
+            flops_step = 23.52e12 * batch / 32
+        else:
+            batch, n, hw = args.batch or 1, 1, (192, 320)
+            flops_step = 0.060e12 * batch
+        store = ParamStore(m, device=dev, with_optimizer_state=False)
+        store.init_reference(seed=0)
+        image = torch.rand(batch * n, hw[0], hw[1], 3, generator=g).to(torch.bfloat16).to(dev)
+        ids = torch.randint(100, 50357, (batch, n, 32), generator=g, dtype=torch.int32)
+        ids[:, :, 0] = 2
+        ids[:, :, 24:] = 0
+        ids = ids.to(dev)
+        shuf = (torch.stack([torch.randperm(n, generator=g) for _ in range(batch)]) + 64).int().reshape(-1).to(dev)
+        segs = batch * n
+
+        def step():
+            if args.config == 1:
+                mm = MerlotModel(m, is_training=False, use_tpu=False, image=image, input_ids=ids[:, 0], params=store)
+                return mm.encoder_hidden_states["lang"]
+            mm = MerlotModel(m, is_training=False, use_tpu=False, image=image, input_ids=ids, mask_input=False,
+                             shuffled_idx_img=shuf, params=store)
+            H = m["hidden_size"]
+            hl = mm.encoder_hidden_states["lang"].reshape(mm.B, n, mm.lang_chunk_length, H)[:, :, 0]
+            hv = mm.encoder_hidden_states["viz"].reshape(mm.B, n, mm.viz_chunk_length, H)[:, :, 0]
+            return torch.softmax(mm.allpairs_temporal_logits(hl, hv, scope_name="lang_viz_temporal"), -1)
+        what = ("configs[3]: sort_story zero-shot forward, 5 x 384x384 frames per story + all-pairs temporal softmax, eval mode"
+                if args.config == 4 else "configs[0]: MerlotModel forward, 1 frame 192x320 + 32 text tokens (2-D ids), eval mode")
+        metric = "frame-caption segments/sec (forward)"
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    L.lib().merlot_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.dist.all_reduce(ms, op=dist.dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        t = float(ms) / args.steps
+        tf = flops_step / (t * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": metric, "value": segs * world / (t * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": what, "global_batch": batch * world, "segments_per_step": segs * world, "parallelism": f"dp{world}",
+                       "l2": "working set far larger than the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": int(L.lib().merlot_launch_count()),
+            "roofline": {"bound": "tensor", "kernel": "whole step (algorithmic FLOPs of SURVEY 8(d) / step time)", "achieved": tf,
+                         "peak": sustained, "unit": "TFLOP/s", "frac": tf / sustained, "traffic": None,
+                         "peak_source": f"{how} bf16_tflops_sustained"},
+            "e2e": None, "cpu_baseline": None}), flush=True)
+    if dist is not None:
+        dist.barrier()
+
+
 def attention_rates(dev):
     """K2 (forward) and K3 (backward incl. dsum / dq finish) alone, CUDA-event timed, at the ViT shape of configs[1]
     (32 frames x 266 tokens) and the joint-encoder shape of SURVEY 8(d) cfg5 (16 x 3608 tokens, key mask off); algorithmic
@@ -370,7 +474,7 @@ def attention_rates(dev):
         dctx = (torch.randn(B * S, H, generator=g) * 0.5).to(torch.bfloat16).to(dev)
         ctx, lse = ops.attention_fwd(qkv, B, S, heads)
         dqkv = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=dev)
-        dq_acc = torch.zeros(B * S, H, dtype=torch.float32, device=dev)  # K3 hands it back zeroed
+        dq_acc = ops.attention_bwd_workspace(B, S, heads, dev)  # K3 hands it back zeroed
         dsum = torch.empty(B, heads, S, dtype=torch.float32, device=dev)
         ops.attention_bwd(qkv, ctx, dctx, lse, B, S, heads, dqkv=dqkv, dq_accum=dq_acc, dsum=dsum)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -398,9 +502,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4, 5],
+                    help="BASELINE.json configs, 1-based as SURVEY 8 numbers them: 2 (default) = the headline 4-segment pretrain step")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override for --config 1/4/5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 2:
+        run_other_config(args)
     else:
         run_ours(args)
 

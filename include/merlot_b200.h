@@ -89,8 +89,11 @@ int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream);
  *          utils/vision_transformer.py).  mask[q,k] = valid[q] & valid[k] (model/modeling.py:158).
  *  lse   : f32 [B, heads, S] log-sum-exp of the masked scaled scores (written by fwd, read by bwd / colsum).
  *  fwd   : ctx bf16 [B*S, ld_ctx] <- softmax(.) v
- *  bwd   : needs ctx, d_ctx (bf16 [B*S, ld_ctx]); writes dsum (scratch f32 [B,heads,S]), accumulates dq in dq_accum
- *          (f32 [B*S, ld_dq], MUST be zero on entry; it is re-zeroed on exit) and writes dqkv bf16 [B*S, ld_dqkv];
+ *  bwd   : needs ctx, d_ctx (bf16 [B*S, ld_ctx]); writes dsum (scratch f32 [B,heads,S]) and dqkv bf16 [B*S, ld_dqkv].
+ *          dq_accum is an fp32 workspace of merlot_attention_bwd_workspace_bytes(B,S,heads) bytes with row stride ld_dq (= H):
+ *          for sequences of <= 4 key tiles (merlot_attention_bwd_dq_parts(S) > 0) every key tile stores its dQ partial into its
+ *          own [B*S, ld_dq] slice (no atomics, bitwise reproducible, no initialisation needed); longer sequences red.add into
+ *          ONE slice that MUST be zero on entry and is re-zeroed on exit;
  *          with d_bias_qkv != NULL the same pass adds colsum(dqkv) to it (bias gradient of the q/k/v tf.layers.dense).
  *  colsum: colsum[b,k] += (1/heads) * sum_q P[b,h,q,k]   (f32 [B,S]; caller zeroes it once per stack).
  * ------------------------------------------------------------------------------------------------------------ */
@@ -114,6 +117,8 @@ typedef struct merlot_attn {
 
 int merlot_attention_fwd(const merlot_attn_t* a, void* stream);
 int merlot_attention_bwd(const merlot_attn_t* a, void* stream);
+int merlot_attention_bwd_dq_parts(int S);                          /* slices used by bwd for this S; 0 = atomic single slice */
+size_t merlot_attention_bwd_workspace_bytes(int B, int S, int heads); /* bytes of dq_accum (ld_dq = heads*64) */
 int merlot_attention_colsum(const merlot_attn_t* a, void* stream);
 /* attention_log (model/modeling.py:186-203): out4 = {lang2lang, lang2viz, viz2lang, viz2viz} normalised block sums of the
  * layer/head/batch-mean attention map, from the two split column sums (queries in the viz piece / in the lang piece). */
@@ -223,6 +228,10 @@ typedef struct merlot_stack {
   const void* dy;                              /* bf16 [B*S, H] gradient wrt y */
   void* dh_in;                                 /* bf16 [B*S, H] gradient wrt h_in (optional) */
   void* scratch;                               /* merlot_stack_scratch_bytes() */
+  /* partial backward: layers [bwd_lo, bwd_hi) are walked top-down in this call (0,0 = all).  A call with bwd_hi == layers
+   * starts from dy (final LayerNorm); later calls continue from the gradient left in `scratch` by the previous one, so a
+   * caller can start the gradient all-reduce of a layer group while the groups below it are still running. */
+  int bwd_lo, bwd_hi;
 } merlot_stack_t;
 
 size_t merlot_stack_activation_bytes(const merlot_stack_t* s);

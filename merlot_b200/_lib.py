@@ -69,7 +69,8 @@ def lib() -> C.CDLL:
     l.merlot_abi_version.restype = C.c_int
     l.merlot_launch_count.restype = C.c_longlong
     l.merlot_reset_launch_count.restype = None
-    for fn in ("merlot_stack_activation_bytes", "merlot_stack_scratch_bytes", "merlot_layernorm_bwd_workspace_bytes"):
+    for fn in ("merlot_stack_activation_bytes", "merlot_stack_scratch_bytes", "merlot_layernorm_bwd_workspace_bytes",
+               "merlot_attention_bwd_workspace_bytes"):
         getattr(l, fn).restype = C.c_size_t
     _lib = l
     return l
@@ -164,6 +165,7 @@ class StackDesc(C.Structure):
         ("dy", C.c_void_p),
         ("dh_in", C.c_void_p),
         ("scratch", C.c_void_p),
+        ("bwd_lo", C.c_int), ("bwd_hi", C.c_int),
     ]
 
 

@@ -29,7 +29,8 @@ struct AttnDev {
   float* lse;                    // [B, heads, S] natural-log LSE of the masked, scaled scores
   // backward
   float* dsum;                   // [B, heads, S]  D = rowsum(dO * O)
-  float* dq_accum; int ld_dq;    // fp32 [B*S, H], atomically accumulated
+  float* dq_accum; int ld_dq;    // fp32 [parts][B*S, H]: per-key-tile slices (or one atomically accumulated slice)
+  size_t dq_part_stride;         // elements between slices
   bf16* dqkv; int ld_dqkv;       // bf16 [B*S, 3H]; this kernel writes the K and V column blocks
   // K4
   float* colsum;                 // [B, S] += sum_q mean_h P[b,h,q,k]
@@ -46,13 +47,16 @@ __device__ __forceinline__ float masked_score(float s, float sc2, bool vq, bool 
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// forward.  One CTA per (128-query tile, head, batch); 128 threads = one thread per TMEM lane = one query row.
-// Per 128-key tile:  S = Q K^T (tcgen05) -> the whole S row is read ONCE into registers -> masked online softmax with
-// register bitmasks for key validity -> P (bf16) into a swizzled smem A tile -> O += P V accumulated IN TMEM.
-// The running maximum is only advanced when it grows by more than 2^8 (lazy rescale: O is then corrected in TMEM with
-// tcgen05.ld/st), so the common iteration never touches O.
+// forward (v2).  One CTA per (128-query tile, head, batch); 128 threads = one thread per TMEM lane = one query row; key tiles
+// of 64 so that a CTA needs 128 TMEM columns, ~58 KB of smem and ~64 live score registers per thread: THREE CTAs are resident
+// per SM and one CTA's tensor phase (S = Q K^T, O += P V) runs under the others' softmax phase.
+// Per key tile:  S (tcgen05) -> the S row is read ONCE into registers -> masked online softmax with register bitmasks for key
+// validity -> P (bf16) into a swizzled smem A tile -> O += P V accumulated IN TMEM.  The running maximum only advances when it
+// grows by more than 2^8 (lazy rescale: O is then corrected in TMEM with tcgen05.ld/st), so the common iteration never touches
+// O.  Warps whose 32 query rows all lie past the sequence end (ragged last query tile) skip the softmax arithmetic.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = 16384 * 4 + 32768 + 1024 + 1024;  // Q, K, 2 x V, P, masks + barriers
+constexpr int FK = 64;  // keys per tile
+constexpr int FWD_SMEM = 16384 + 8192 + 2 * 8192 + 16384 + 512 + 128 + 1024;  // Q, K, 2 x V, P, masks, barriers, alignment
 constexpr int MAX_MASK_WORDS = 128;  // key-validity bitmask for up to 4096 keys
 constexpr float MASKED_LOG2 = -1e10f * LOG2E;
 
@@ -63,15 +67,16 @@ __device__ __forceinline__ uint32_t range_word(int k, int S) {
 }
 
 template <bool HAS_MASK>
-__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnDev p) {
+__global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                                                          const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 16384;
-  uint8_t* sV = smem + 32768;  // two V tiles: tile j lives in buffer j & 1 (loaded a whole tile ahead)
-  uint8_t* sP = smem + 65536;  // [128 q rows][128 keys] bf16, two 64-key K-major atoms of 16 KB
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 65536 + 32768);  // [MAX_MASK_WORDS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 65536 + 32768 + 512);
+  uint8_t* sV = smem + 24576;  // two V tiles: tile j lives in buffer j & 1 (loaded a whole tile ahead)
+  uint8_t* sP = smem + 40960;  // [128 q rows][64 keys] bf16: one K-major 128B-swizzled atom
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 57344);  // [MAX_MASK_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 57344 + 512);
   uint64_t *bar_q = bars, *bar_k = bars + 1, *bar_v = bars + 2 /* [2] */, *bar_s = bars + 4, *bar_o = bars + 5;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
@@ -80,17 +85,17 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   pdl_launch_dependents();
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
-  const int n_kv = (S + AT_N - 1) / AT_N;
+  const int n_kv = (S + FK - 1) / FK;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kv);
     mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(&bar_v[0], 1); mbar_init(&bar_v[1], 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
   pdl_wait();
   if (HAS_MASK) {  // key validity of this batch element as a bitmask (bit k%32 of word k/32)
-    for (int k = tid; k < n_kv * AT_N; k += 128) {
+    for (int k = tid; k < n_kv * FK; k += 128) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
       const uint32_t w = __ballot_sync(0xffffffffu, v);
       if (lane == 0) s_mask[k >> 5] = w;
@@ -100,34 +105,34 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem + 64;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, 16384);
-    tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
-    mbar_arrive_expect_tx(bar_k, 16384);
-    tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0);
-    mbar_arrive_expect_tx(&bar_v[0], 16384);
-    tma_load_2d(sV, &tm_qkv, &bar_v[0], 2 * H + h * AT_D, tok0);
+    tma_load_2d(sQ, &tm_q, bar_q, h * AT_D, tok0 + q0);
+    mbar_arrive_expect_tx(bar_k, 8192);
+    tma_load_2d(sK, &tm_kv, bar_k, H + h * AT_D, tok0);
+    mbar_arrive_expect_tx(&bar_v[0], 8192);
+    tma_load_2d(sV, &tm_kv, &bar_v[0], 2 * H + h * AT_D, tok0);
   }
 
   const int q = q0 + tid;
   const bool q_in = q < S;
+  const bool warp_live = (q0 + warp * 32) < S;  // at least one real query row in this warp
   const bool vq = (HAS_MASK && q_in) ? (p.valid[tok0 + q] != 0) : true;
   // a padding QUERY row softmaxes uniformly over all in-range keys: realised as zero scores with every key "valid"
   const float sc2 = vq ? p.scale * LOG2E : 0.f;
   float m_used = -INFINITY, l_run = 0.f;
 
   constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
-  // a ragged last key tile (S = 266: 10 keys) only costs its 32-key chunks: S = Q K^T with N = 32 nck, nck chunks of
-  // softmax, 2 nck k16-steps of P V
-  auto nck_of = [&](int j) { return min(AT_N / 32, (S - j * AT_N + 31) >> 5); };
+  // a ragged last key tile (S = 266: 10 keys) only costs its 16-key units: S = Q K^T with N = 16 nu, nu k16-steps of P V
+  auto nu_of = [&](int j) { return min(FK / 16, (S - j * FK + 15) >> 4); };
   auto issue_s = [&](int j) {  // S_j = Q K_j^T (tid 0); its commit also covers every MMA issued before it
     mbar_wait(bar_k, (uint32_t)(j & 1));
     tc_fence_after();
     const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
-    const uint32_t idesc_s = make_idesc_bf16(AT_M, nck_of(j) * 32, 0, 0);
+    const uint32_t idesc_s = make_idesc_bf16(AT_M, nu_of(j) * 16, 0, 0);
 #pragma unroll
     for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
     umma_commit(bar_s);
@@ -141,81 +146,82 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   // tensor pipe runs them back to back); K_{j+1} and V_{j+1} are fetched while the softmax of tile j runs.
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
-    const int k0 = j * AT_N;
-    const int nck = nck_of(j);
+    const int k0 = j * FK;
+    const int nu = nu_of(j);
     mbar_wait(bar_s, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) {  // S_j and P V_{j-1} have completed: the K tile and V buffer (j+1)&1 are free
-      mbar_arrive_expect_tx(bar_k, 16384);
-      tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + (j + 1) * AT_N);
-      mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], 16384);
-      tma_load_2d(sV + ((j + 1) & 1) * 16384, &tm_qkv, &bar_v[(j + 1) & 1], 2 * H + h * AT_D, tok0 + (j + 1) * AT_N);
+      mbar_arrive_expect_tx(bar_k, 8192);
+      tma_load_2d(sK, &tm_kv, bar_k, H + h * AT_D, tok0 + (j + 1) * FK);
+      mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], 8192);
+      tma_load_2d(sV + ((j + 1) & 1) * 8192, &tm_kv, &bar_v[(j + 1) & 1], 2 * H + h * AT_D, tok0 + (j + 1) * FK);
     }
-    // ---- S row -> registers (log2 domain), masked; row maximum ----
-    float x[AT_N];
-    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max / sum chains instead of a 128-long one
+    if (warp_live) {
+      // ---- S row -> registers (log2 domain), masked; row maximum ----
+      float x[FK];
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent max / sum chains instead of a 64-long one
 #pragma unroll
-    for (int c = 0; c < AT_N / 32; ++c) {
-      if (c >= nck) break;
-      uint32_t r[32];
-      tmem_ld_32x32(tS + lane_off + c * 32, r);
-      tmem_wait_ld();
-      const uint32_t iw = range_word(k0 + c * 32, S);
-      const uint32_t vw = (HAS_MASK && vq) ? s_mask[(k0 >> 5) + c] : 0xffffffffu;
-      if (iw == 0xffffffffu && vw == 0xffffffffu) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          x[c * 32 + i] = __uint_as_float(r[i]) * sc2;
-          mx4[i & 3] = fmaxf(mx4[i & 3], x[c * 32 + i]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(r[i]) * sc2;
-          t = ((vw >> i) & 1u) ? t : MASKED_LOG2;
-          t = ((iw >> i) & 1u) ? t : -INFINITY;
-          x[c * 32 + i] = t;
-          mx4[i & 3] = fmaxf(mx4[i & 3], t);
-        }
-      }
-    }
-    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-    // ---- lazy running max: advance (and correct O in TMEM) only when the row max grew by more than 2^8 ----
-    const bool need = mx > m_used + 8.0f;  // always true on the first tile (m_used = -inf)
-    if (j > 0 && __any_sync(0xffffffffu, need)) {
-      const float f = need ? ex2_approx(m_used - mx) : 1.0f;
-#pragma unroll
-      for (int c = 0; c < AT_D / 32; ++c) {
+      for (int c = 0; c < FK / 32; ++c) {
+        if (c * 2 >= nu) break;
         uint32_t r[32];
-        tmem_ld_32x32(tO + lane_off + c * 32, r);
+        tmem_ld_32x32(tS + lane_off + c * 32, r);  // (columns past N = 16 nu hold stale scores: masked to -inf below)
         tmem_wait_ld();
+        const uint32_t iw = range_word(k0 + c * 32, S);
+        const uint32_t vw = (HAS_MASK && vq) ? s_mask[(k0 >> 5) + c] : 0xffffffffu;
+        if (iw == 0xffffffffu && vw == 0xffffffffu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-        tmem_st_32x32(tO + lane_off + c * 32, r);
+          for (int i = 0; i < 32; ++i) {
+            x[c * 32 + i] = __uint_as_float(r[i]) * sc2;
+            mx4[i & 3] = fmaxf(mx4[i & 3], x[c * 32 + i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = __uint_as_float(r[i]) * sc2;
+            t = ((vw >> i) & 1u) ? t : MASKED_LOG2;
+            t = ((iw >> i) & 1u) ? t : -INFINITY;
+            x[c * 32 + i] = t;
+            mx4[i & 3] = fmaxf(mx4[i & 3], t);
+          }
+        }
       }
-      tmem_wait_st();
-      l_run *= f;
-    }
-    if (need) m_used = mx;
-    // ---- p = 2^(x - m), P (bf16) into the K-major swizzled A tile ----
-    float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // ---- lazy running max: advance (and correct O in TMEM) only when the row max grew by more than 2^8 ----
+      const bool need = mx > m_used + 8.0f;  // always true on the first tile (m_used = -inf)
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        const float f = need ? ex2_approx(m_used - mx) : 1.0f;
 #pragma unroll
-    for (int c = 0; c < AT_N / 32; ++c) {
-      if (c >= nck) break;
-      uint32_t pk[16];
+        for (int c = 0; c < AT_D / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tO + lane_off + c * 32, r);
+          tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(x[c * 32 + i] - m_used), p1 = ex2_approx(x[c * 32 + i + 1] - m_used);
-        rs4[(i >> 1) & 3] += p0 + p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st_32x32(tO + lane_off + c * 32, r);
+        }
+        tmem_wait_st();
+        l_run *= f;
       }
-      uint8_t* atom = sP + (c >> 1) * 16384;
+      if (need) m_used = mx;
+      // ---- p = 2^(x - m), P (bf16) into the K-major swizzled A tile ----
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(atom + sw128_offset(tid, (uint32_t)((c & 1) * 4 + g))) =
-            make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+      for (int c = 0; c < FK / 32; ++c) {
+        if (c * 2 >= nu) break;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(x[c * 32 + i] - m_used), p1 = ex2_approx(x[c * 32 + i + 1] - m_used);
+          rs4[(i >> 1) & 3] += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(sP + sw128_offset(tid, (uint32_t)(c * 4 + g))) =
+              make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+      }
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
     }
-    l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -223,13 +229,11 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
       tc_fence_after();
       mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (j & 1) * 16384);
+      const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (j & 1) * 8192);
 #pragma unroll
-      for (int k = 0; k < AT_N / 16; ++k) {
-        if (k >= 2 * nck) break;
-        const uint64_t da = desc_kmajor(pa + (k >> 2) * 16384, k & 3);
-        const uint64_t db = desc_mnmajor(va, k, 0);  // single 64-wide chunk: LBO unused
-        umma_bf16_ss(tO, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < FK / 16; ++k) {
+        if (k >= nu) break;
+        umma_bf16_ss(tO, desc_kmajor(pa, k), desc_mnmajor(va, k, 0), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
       }
       if (j + 1 < n_kv) issue_s(j + 1);  // commits bar_s: P V_j and S_{j+1}
       else umma_commit(bar_o);
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   mbar_wait(bar_o, 0);  // last P V: O is final
   tc_fence_after();
 
-  {
+  if (warp_live) {
     const float inv = 1.0f / l_run;
     bf16* dst = p.ctx + (size_t)(tok0 + q) * p.ld_ctx + h * AT_D;
 #pragma unroll
@@ -261,63 +265,80 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// backward: one CTA per (key tile, head, batch); loops over query tiles (double-buffered Q/dO, prefetched by TMA).
-//   S^T = K Q^T, dP^T = V dO^T (keys on TMEM lanes) -> P^T, dS^T in smem -> dV += P^T dO, dK += dS^T Q, dQ_i = dS K
-// The S^T/dP^T MMAs of tile i+1 are issued right behind the dV/dK/dQ MMAs of tile i, so the tensor pipe works while the
-// threads red.add the dQ partial of tile i.
+// backward (v2): one CTA per (128-key tile, head, batch), TWO CTAs resident per SM (256 TMEM columns, ~100 KB smem each) so
+// that one CTA's tensor phase runs under the other's softmax phase.  Keys sit on the TMEM lanes; the queries are walked in
+// chunks of 64 (double-buffered Q/dO, prefetched by TMA):
+//   S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T (bf16, swizzled smem)  ->  dV += P^T dO, dK += dS^T Q (TMEM, whole key tile),
+//   dQ_chunk = dS K  (M = 64 accumulator: rows 16w..16w+15 live on lanes 32w..32w+15, "half subpartition" layout).
+// dQ never touches an atomic when the sequence has <= 4 key tiles: every CTA stores its partial for its key tile into its own
+// slice of the [parts][tokens][H] fp32 workspace (plain coalesced stores) and attn_dqkv_finish sums the slices; longer
+// sequences red.add into one slice.  Warps whose 32 keys all lie past the sequence end (ragged last key tile: S = 266 has 10
+// keys there) zero their P^T / dS^T rows once and skip the softmax arithmetic.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 16384 * 2 + 32768 * 2 + 32768 * 2 + 2048 + 1024 + 1024;
+constexpr int BQ = 64;              // queries per chunk
+constexpr int MAX_DQ_PARTS = 4;     // key tiles per sequence for which dQ goes through per-tile slices instead of atomics
+constexpr int BWD_SMEM = 16384 * 2 + 2 * 16384 + 16384 * 2 + 1024 + 512 + 128 + 1024;
 
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
+template <bool HAS_MASK, bool DQ_ATOMIC>
+__global__ void __launch_bounds__(256, 2)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
+                const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQd = smem + 32768;            // 2 x { Q tile 16 KB, dO tile 16 KB }
-  uint8_t* sPT = smem + 32768 + 65536;    // P^T  [128 keys][128 q] bf16, two 64-col atoms
-  uint8_t* sdST = sPT + 32768;            // dS^T same layout
-  float* s_nlse = reinterpret_cast<float*>(sdST + 32768);  // [2][128]  -lse * log2(e)
-  float* s_dsum = s_nlse + 256;                            // [2][128]
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 256);  // [MAX_MASK_WORDS]
+  uint8_t* sQd = smem + 32768;            // 2 x { Q chunk 8 KB, dO chunk 8 KB }
+  uint8_t* sPT = smem + 32768 + 32768;    // P^T  [128 keys][64 q] bf16: one 128B-swizzled atom
+  uint8_t* sdST = sPT + 16384;            // dS^T same layout
+  float* s_nlse = reinterpret_cast<float*>(sdST + 16384);  // [2][64]  -lse * log2(e)
+  float* s_dsum = s_nlse + 128;                            // [2][64]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 128);  // [MAX_MASK_WORDS]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_mask) + 512);
   uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [2] */, *bar_1 = bars + 3, *bar_2 = bars + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
-  // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every tile's columns
+  // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every chunk's columns
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3, row_t = quad * 32 + lane;
   pdl_launch_dependents();
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
   const int tok0 = b * S;
-  const int n_q = (S + AT_M - 1) / AT_M;
+  const int n_q = (S + BQ - 1) / BQ;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do);
     mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_1, 1); mbar_init(bar_2, 1);
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
+  // a warp whose 32 keys are all out of range contributes exact zeros: written once, arithmetic skipped afterwards
+  const bool warp_dead = (k0 + quad * 32) >= S;
+  if (warp_dead && wg == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      *reinterpret_cast<uint4*>(sPT + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sdST + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   pdl_wait();
   if (HAS_MASK) {
-    for (int k = tid; k < n_q * AT_M; k += 256) {
+    for (int k = tid; k < n_q * BQ; k += 256) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
       const uint32_t w = __ballot_sync(0xffffffffu, v);
       if (lane == 0) s_mask[k >> 5] = w;
     }
   }
-  auto stage_stats = [&](int i) {  // -lse*log2e and D of query tile i -> smem buffer i&1
-    if (tid < 128) {
-      const int q = i * AT_M + tid;
+  auto stage_stats = [&](int i) {  // -lse*log2e and D of query chunk i -> smem buffer i&1
+    if (tid < BQ) {
+      const int q = i * BQ + tid;
       const size_t o = ((size_t)b * p.heads + h) * S + q;
-      s_nlse[(i & 1) * 128 + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
-      s_dsum[(i & 1) * 128 + tid] = (q < S) ? p.dsum[o] : 0.f;
+      s_nlse[(i & 1) * BQ + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
+      s_dsum[(i & 1) * BQ + tid] = (q < S) ? p.dsum[o] : 0.f;
     }
   };
   stage_stats(0);
@@ -325,26 +346,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
-  const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const uint32_t tST = tmem, tdPT = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tdQ = tmem;  // dQ reuses the S^T columns
   const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
-  // a ragged last query tile only costs its 32-query chunks (S^T / dP^T with N = 32 ncq, ncq softmax chunks, 2 ncq k16-steps
-  // of dV / dK); dQ keeps its 128 rows (TMEM lanes) -- the rows past S are computed from stale dS^T columns and never stored
-  auto ncq_of = [&](int i) { return min(AT_M / 32, (S - i * AT_M + 31) >> 5); };
+  // a ragged last chunk only costs its 16-query units (S^T / dP^T with N = 16 nu, nu softmax units, nu k16-steps of dV / dK)
+  auto nu_of = [&](int i) { return min(BQ / 16, (S - i * BQ + 15) >> 4); };
   constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
-  constexpr uint32_t idesc_dq = make_idesc_bf16(AT_M, AT_D, 1, 1);   // A = dS (MN-major view of dS^T), B = K MN-major
+  constexpr uint32_t idesc_dq = make_idesc_bf16(BQ, AT_D, 1, 1);     // M = 64: A = dS (MN-major view of dS^T), B = K MN-major
 
   auto load_q = [&](int i) {
-    uint8_t* buf = sQd + (i & 1) * 32768;
-    mbar_arrive_expect_tx(&bar_q[i & 1], 32768);
-    tma_load_2d(buf, &tm_qkv, &bar_q[i & 1], h * AT_D, tok0 + i * AT_M);
-    tma_load_2d(buf + 16384, &tm_do, &bar_q[i & 1], h * AT_D, tok0 + i * AT_M);
+    uint8_t* buf = sQd + (i & 1) * 16384;
+    mbar_arrive_expect_tx(&bar_q[i & 1], 16384);
+    tma_load_2d(buf, &tm_q, &bar_q[i & 1], h * AT_D, tok0 + i * BQ);
+    tma_load_2d(buf + 8192, &tm_do, &bar_q[i & 1], h * AT_D, tok0 + i * BQ);
   };
-  auto issue_st = [&](int i) {  // S^T and dP^T of query tile i
+  auto issue_st = [&](int i) {  // S^T and dP^T of query chunk i
     mbar_wait(&bar_q[i & 1], (uint32_t)((i >> 1) & 1));
     tc_fence_after();
-    const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQd + (i & 1) * 32768), da = qa + 16384;
-    const uint32_t idesc_st = make_idesc_bf16(AT_N, ncq_of(i) * 32, 0, 0);  // S^T, dP^T : both operands K-major (d)
+    const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQd + (i & 1) * 16384), da = qa + 8192;
+    const uint32_t idesc_st = make_idesc_bf16(AT_N, nu_of(i) * 16, 0, 0);  // S^T, dP^T : both operands K-major (d)
 #pragma unroll
     for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
 #pragma unroll
@@ -354,8 +374,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_kv, 32768);
-    tma_load_2d(sK, &tm_qkv, bar_kv, H + h * AT_D, tok0 + k0);
-    tma_load_2d(sV, &tm_qkv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
+    tma_load_2d(sK, &tm_kv, bar_kv, H + h * AT_D, tok0 + k0);
+    tma_load_2d(sV, &tm_kv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
     load_q(0);
     if (n_q > 1) load_q(1);
     mbar_wait(bar_kv, 0);
@@ -365,52 +385,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   const bool k_in = kk < S;
   const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
   const float sc2 = p.scale * LOG2E;
+  float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)blockIdx.x * p.dq_part_stride);
 
   for (int i = 0; i < n_q; ++i) {
     const uint32_t ph = i & 1;
-    const int q0 = i * AT_M;
-    const float* nlse = s_nlse + (i & 1) * 128;
-    const float* dsm = s_dsum + (i & 1) * 128;
-    const int ncq = ncq_of(i);
+    const int q0 = i * BQ;
+    const float* nlse = s_nlse + (i & 1) * BQ;
+    const float* dsm = s_dsum + (i & 1) * BQ;
+    const int nu = nu_of(i);
     mbar_wait(bar_1, ph);
     tc_fence_after();
+    if (!warp_dead) {
 #pragma unroll 1
-    for (int c = wg * 2; c < wg * 2 + 2; ++c) {
-      if (c >= ncq) break;  // warp-uniform
-      uint32_t rs[32], rd[32];
-      tmem_ld_32x32(tST + lane_off + c * 32, rs);
-      tmem_ld_32x32(tdPT + lane_off + c * 32, rd);
-      tmem_wait_ld();
-      const uint32_t iw = k_in ? range_word(q0 + c * 32, S) : 0u;           // query in range (and this key in range)
-      const uint32_t qw = HAS_MASK ? s_mask[(q0 >> 5) + c] : 0xffffffffu;   // query validity
-      const bool fast = (iw == 0xffffffffu) && (qw == 0xffffffffu) && vk;
-      uint32_t pk[16], dk[16];
+      for (int u = wg * 2; u < wg * 2 + 2; ++u) {
+        if (u >= nu) break;  // warp-uniform
+        uint32_t rs[16], rd[16];
+        tmem_ld_32x16(tST + lane_off + u * 16, rs);
+        tmem_ld_32x16(tdPT + lane_off + u * 16, rd);
+        tmem_wait_ld();
+        const int qb = q0 + u * 16;
+        const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
+        const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
+        const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
+        uint32_t pk[8], dk[8];
 #pragma unroll
-      for (int e = 0; e < 32; e += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(nlse + c * 32 + e);
-        const float4 d4 = *reinterpret_cast<const float4*>(dsm + c * 32 + e);
-        const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
-        float pv[4], dv[4];
+        for (int e = 0; e < 16; e += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(nlse + u * 16 + e);
+          const float4 d4 = *reinterpret_cast<const float4*>(dsm + u * 16 + e);
+          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+          float pv[4], dv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float t = __uint_as_float(rs[e + u]) * sc2;
-          if (!fast) {
-            t = vk ? t : MASKED_LOG2;
-            t = ((qw >> (e + u)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
+          for (int t4 = 0; t4 < 4; ++t4) {
+            float t = __uint_as_float(rs[e + t4]) * sc2;
+            if (!fast) {
+              t = vk ? t : MASKED_LOG2;
+              t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
+            }
+            float pr = ex2_approx(t + ls[t4]);
+            if (!fast) pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
+            pv[t4] = pr;
+            // d(score)/d(q k^T) = m * scale (utils/transformer.py:109-110: scores*m - 1e10*(1-m)): a padding QUERY row keeps its
+            // uniform probabilities for dV but sends nothing back into q and k
+            float g = pr * p.scale;
+            if (!fast) g = ((qw >> (e + t4)) & 1u) ? g : 0.f;
+            dv[t4] = (__uint_as_float(rd[e + t4]) - ds[t4]) * g;
           }
-          float pr = ex2_approx(t + ls[u]);
-          if (!fast) pr = ((iw >> (e + u)) & 1u) ? pr : 0.f;
-          pv[u] = pr;
-          dv[u] = (__uint_as_float(rd[e + u]) - ds[u]) * (pr * p.scale);
+          pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+          dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
         }
-        pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-        dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
-      }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t off = (uint32_t)(c >> 1) * 16384 + sw128_offset(row_t, (uint32_t)((c & 1) * 4 + g));
-        *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-        *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t off = sw128_offset(row_t, (uint32_t)(u * 2 + g));
+          *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+          *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+        }
       }
     }
     if (i + 1 < n_q) stage_stats(i + 1);
@@ -419,43 +447,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQd + (i & 1) * 32768), da = qa + 16384,
+      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQd + (i & 1) * 16384), da = qa + 8192,
                      ka = smem_u32(sK);
 #pragma unroll
-      for (int k = 0; k < AT_M / 16; ++k)  // dV += P^T dO   (contraction over q)
-        if (k < 2 * ncq) umma_bf16_ss(tdV, desc_kmajor(pa + (k >> 2) * 16384, k & 3), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
+      for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (contraction over q)
+        if (k < nu) umma_bf16_ss(tdV, desc_kmajor(pa, k), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
 #pragma unroll
-      for (int k = 0; k < AT_M / 16; ++k)  // dK += dS^T Q
-        if (k < 2 * ncq) umma_bf16_ss(tdK, desc_kmajor(sa + (k >> 2) * 16384, k & 3), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
+      for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
+        if (k < nu) umma_bf16_ss(tdK, desc_kmajor(sa, k), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
 #pragma unroll
-      for (int k = 0; k < AT_N / 16; ++k)  // dQ_i = dS K      (contraction over keys; A = MN-major view of dS^T)
-        umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 16384), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);
+      for (int k = 0; k < AT_N / 16; ++k)  // dQ_chunk = dS K  (contraction over the 128 keys; stale columns of a ragged chunk
+        umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 0), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);  // only feed rows that are never stored)
       umma_commit(bar_2);
-      if (i + 1 < n_q) issue_st(i + 1);  // keeps the tensor pipe busy during the dQ reduction below
     }
     mbar_wait(bar_2, ph);
     tc_fence_after();
     if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
-    {  // dQ partial: lanes are query rows here
-      const int q = q0 + row_t;
-      {
-        const int c = wg;
-        uint32_t r[32];
-        tmem_ld_32x32(tdQ + lane_off + c * 32, r);
-        tmem_wait_ld();
-        if (q < S) {
-          float* dst = p.dq_accum + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + c * 32;
+    {  // dQ partial of this key tile: M = 64 accumulator, row 16*quad + l lives on lane 32*quad + l (l < 16)
+      const int q = q0 + quad * 16 + lane;
+      uint32_t r[32];
+      tmem_ld_32x32(tdQ + lane_off + wg * 32, r);
+      tmem_wait_ld();
+      if (lane < 16 && q < S) {
+        float* dst = dq_base + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + wg * 32;
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
+        for (int g = 0; g < 8; ++g) {
+          if (DQ_ATOMIC) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
                          "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
                          "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
                          : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
+                                                                  __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+          }
         }
       }
     }
     tc_fence_before();
-    __syncthreads();  // dQ TMEM / P^T, dS^T smem reuse by the next iteration
+    __syncthreads();  // dQ TMEM (= S^T columns) / P^T, dS^T smem are reused by the next chunk
+    if (tid == 0 && i + 1 < n_q) { tc_fence_after(); issue_st(i + 1); }
   }
   // ---- dK, dV for this key tile (exclusive rows) ----
   tc_fence_after();
@@ -482,7 +513,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // D[b,h,q] = sum_d dO[q,hd] * O[q,hd]   (one warp per (token, head) pair would waste lanes; 8 lanes x 8 elems per head)
@@ -522,8 +553,11 @@ __global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restr
 
 // dq fp32 accumulator -> bf16 q-block of dqkv (and re-zero the accumulator for the next layer), fused with the column sums
 // of the whole dqkv row block = the gradient of the fused q/k/v bias.  grid = (ceil(3H/256), row slabs), 8 warps, lane = 8 cols.
+// n_parts > 0: dq holds n_parts per-key-tile slices (part_stride elements apart) that are summed here; n_parts == 0: one
+// atomically accumulated slice that is re-zeroed for the next layer.
 __global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv,
-                                                               long long rows, int H, float* __restrict__ bias_grad) {
+                                                               long long rows, int H, float* __restrict__ bias_grad, int n_parts,
+                                                               size_t part_stride) {
   __shared__ float sred[8][256];
   pdl_launch_dependents();
   pdl_wait();
@@ -536,11 +570,20 @@ __global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict
       bf16* o = dqkv + (size_t)r * ld_dqkv + col;
       if (col < H) {
         float4* src = reinterpret_cast<float4*>(dq + (size_t)r * ld_dq + col);
-        const float4 a = src[0], b = src[1];
+        float4 a = src[0], b = src[1];
+        if (n_parts == 0) {
+          src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          for (int t = 1; t < n_parts; ++t) {  // fixed order: the sum is bitwise reproducible
+            const float4* s2 = reinterpret_cast<const float4*>(dq + (size_t)t * part_stride + (size_t)r * ld_dq + col);
+            const float4 c = s2[0], d = s2[1];
+            a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+            b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
+          }
+        }
         const uint4 pk = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
         *reinterpret_cast<uint4*>(o) = pk;
-        src[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         const uint32_t* pu = reinterpret_cast<const uint32_t*>(&pk);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const float2 f = unpack_bf16x2(pu[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
@@ -568,95 +611,130 @@ __global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict
 
 // -----------------------------------------------------------------------------------------------------------------
 // K4: colsum[b,k] += (1/heads) * sum_q P[b,h,q,k], recomputed from (q,k,lse); keys on TMEM lanes so the reduction over
-// queries runs along registers.  One CTA per (key tile, head, batch).
+// queries runs along registers.  One CTA per (key tile, head, batch), two resident per SM; the query tiles are double-buffered
+// in smem AND in TMEM: S^T of tile i+1 is issued before the exponentials of tile i start.
 // -----------------------------------------------------------------------------------------------------------------
-constexpr int CS_SMEM = 16384 * 2 + 1024 + 512 + 128;
+constexpr int CS_SMEM = 16384 * 3 + 1024 + 512 + 128 + 1024;
 
+template <bool HAS_MASK>
 __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
-  uint8_t* sQ = smem + 16384;
-  float* s_lse = reinterpret_cast<float*>(smem + 32768);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 512);
-  uint64_t *bar_k = bars, *bar_q = bars + 1, *bar_s = bars + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* sQ = smem + 16384;                                         // [2] x 16 KB
+  float* s_nlse = reinterpret_cast<float*>(smem + 49152);             // [2][128]  -lse * log2(e)
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + 49152 + 1024);  // query validity bits
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152 + 1024 + 512);
+  uint64_t *bar_k = bars, *bar_q = bars + 1 /* [2] */, *bar_s = bars + 3 /* [2] */;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H, tok0 = b * S;
   const int n_q = (S + AT_M - 1) / AT_M;
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
-    mbar_init(bar_k, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1);
+    mbar_init(bar_k, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
     fence_barrier_init();
   }
   pdl_launch_dependents();
-  if (warp == 0) { tmem_alloc(tmem_ptr, 128); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
   pdl_wait();
+  if (HAS_MASK) {
+    for (int k = tid; k < n_q * AT_M; k += 128) {
+      const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
+      const uint32_t w = __ballot_sync(0xffffffffu, v);
+      if (lane == 0) s_mask[k >> 5] = w;
+    }
+  }
+  auto stage_lse = [&](int i) {
+    const int q = i * AT_M + tid;
+    s_nlse[(i & 1) * AT_M + tid] = (q < S) ? -p.lse[((size_t)b * p.heads + h) * S + q] * LOG2E : 0.f;
+  };
+  stage_lse(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  auto load_q = [&](int i) {
+    mbar_arrive_expect_tx(&bar_q[i & 1], 16384);
+    tma_load_2d(sQ + (i & 1) * 16384, &tm_qkv, &bar_q[i & 1], h * AT_D, tok0 + i * AT_M);
+  };
+  auto ncq_of = [&](int i) { return min(AT_M / 32, (S - i * AT_M + 31) >> 5); };
+  auto issue = [&](int i) {  // S^T of query tile i -> TMEM buffer i & 1
+    mbar_wait(&bar_q[i & 1], (uint32_t)((i >> 1) & 1));
+    tc_fence_after();
+    const uint32_t ka = smem_u32(sK), qa = smem_u32(sQ + (i & 1) * 16384);
+    const uint32_t idesc = make_idesc_bf16(AT_N, ncq_of(i) * 32, 0, 0);
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem + (i & 1) * 128, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc, k > 0);
+    umma_commit(&bar_s[i & 1]);
+  };
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_k, 16384);
     tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + k0);
+    load_q(0);
+    if (n_q > 1) load_q(1);
+    mbar_wait(bar_k, 0);
+    issue(0);
   }
   const int kk = k0 + tid;
   const bool k_in = kk < S;
-  const bool vk = k_in ? (p.valid ? p.valid[tok0 + kk] != 0 : true) : false;
-  constexpr uint32_t idesc = make_idesc_bf16(AT_N, AT_M, 0, 0);
+  const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
+  const bool warp_live = (k0 + warp * 32) < S;
   const float sc2 = p.scale * LOG2E;
   float acc = 0.f, acc2 = 0.f;
   const int split = p.colsum2 ? p.colsum_split : 0x7fffffff;
   for (int i = 0; i < n_q; ++i) {
-    const uint32_t ph = i & 1;
     const int q0 = i * AT_M;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(bar_q, 16384);
-      tma_load_2d(sQ, &tm_qkv, bar_q, h * AT_D, tok0 + q0);
-    }
-    {
-      const int q = q0 + tid;
-      s_lse[tid] = (q < S) ? p.lse[((size_t)b * p.heads + h) * S + q] * LOG2E : 0.f;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (i == 0) mbar_wait(bar_k, 0);
-      mbar_wait(bar_q, ph);
-      tc_fence_after();
-      const uint32_t ka = smem_u32(sK), qa = smem_u32(sQ);
-#pragma unroll
-      for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc, k > 0);
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
+    if (tid == 0 && i + 1 < n_q) issue(i + 1);   // runs under the exponentials below
+    if (i + 1 < n_q) stage_lse(i + 1);
+    mbar_wait(&bar_s[i & 1], (uint32_t)((i >> 1) & 1));
     tc_fence_after();
+    if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // S^T_i has consumed Q buffer i & 1
+    const float* nl = s_nlse + (i & 1) * AT_M;
+    const int ncq = ncq_of(i);
+    if (warp_live) {
 #pragma unroll 1
-    for (int c = 0; c < AT_M / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem + lane_off + c * 32, r);
-      tmem_wait_ld();
+      for (int c = 0; c < AT_M / 32; ++c) {
+        if (c >= ncq) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + (i & 1) * 128 + lane_off + c * 32, r);
+        tmem_wait_ld();
+        const uint32_t iw = k_in ? range_word(q0 + c * 32, S) : 0u;              // query (and this key) in range
+        const uint32_t qw = HAS_MASK ? s_mask[(q0 >> 5) + c] : 0xffffffffu;      // query validity
+        const uint32_t sw = range_word(q0 + c * 32, split);                     // query < split -> colsum, else colsum2
+        const uint32_t keep = iw & ((HAS_MASK && p.colsum_valid_q) ? qw : 0xffffffffu);  // queries that contribute at all
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        if (keep == 0xffffffffu && qw == 0xffffffffu && vk && (sw == 0xffffffffu || sw == 0u)) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int ql = c * 32 + e, q = q0 + ql;
-        if (q < S && k_in) {
-          const bool vq = p.valid ? p.valid[tok0 + q] != 0 : true;
-          float x = masked_score(__uint_as_float(r[e]), sc2, vq, vk, true);
-          const float pr = (p.colsum_valid_q && !vq) ? 0.f : exp2f(x - s_lse[ql]);
-          if (q < split) acc += pr; else acc2 += pr;
+          for (int e = 0; e < 32; e += 2) {
+            a0 += ex2_approx(fmaf(__uint_as_float(r[e]), sc2, nl[c * 32 + e]));
+            a1 += ex2_approx(fmaf(__uint_as_float(r[e + 1]), sc2, nl[c * 32 + e + 1]));
+          }
+          if (sw) acc += a0 + a1; else acc2 += a0 + a1;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float x = __uint_as_float(r[e]) * sc2;
+            x = vk ? x : MASKED_LOG2;
+            x = ((qw >> e) & 1u) ? x : 0.f;  // padding query: uniform row (zero scores)
+            float pr = ex2_approx(x + nl[c * 32 + e]);
+            pr = ((keep >> e) & 1u) ? pr : 0.f;
+            if ((sw >> e) & 1u) a0 += pr; else b0 += pr;
+          }
+          acc += a0; acc2 += b0;
         }
       }
     }
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // TMEM buffer i & 1 and s_nlse[i & 1] are reused two tiles later
   }
   if (k_in) {
     atomicAdd(p.colsum + (size_t)b * S + kk, acc / (float)p.heads);
     if (p.colsum2) atomicAdd(p.colsum2 + (size_t)b * S + kk, acc2 / (float)p.heads);
   }
-  __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 static int check_common(const merlot_attn_t* a) {
@@ -695,8 +773,10 @@ extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
   if (rc) return rc;
   MB_REQUIRE(a->ctx != nullptr && (a->ld_ctx % 8) == 0, MERLOT_EINVAL, "attention_fwd: ctx missing or ld_ctx %% 8 != 0");
   AttnDev p; fill_dev(a, &p);
-  CUtensorMap tm;
-  rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, 128);
+  CUtensorMap tq, tkv;
+  rc = make_tmap_bf16_2d(&tq, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, AT_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tkv, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, FK);
   if (rc) return rc;
   MB_REQUIRE(a->S <= MAX_MASK_WORDS * 32 - AT_N, MERLOT_ESHAPE, "attention_fwd: sequence longer than %d keys", MAX_MASK_WORDS * 32 - AT_N);
   static bool attr = false;
@@ -706,10 +786,20 @@ extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
     attr = true;
   }
   dim3 grid(ceil_div(a->S, AT_M), a->heads, a->B);
-  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), FWD_SMEM, stream, tm, p));
-  else MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), FWD_SMEM, stream, tm, p));
+  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), FWD_SMEM, stream, tq, tkv, p));
+  else MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), FWD_SMEM, stream, tq, tkv, p));
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
+}
+
+extern "C" int merlot_attention_bwd_dq_parts(int S) {
+  const int n_kv = ceil_div(S, AT_N);
+  return n_kv <= MAX_DQ_PARTS ? n_kv : 0;
+}
+
+extern "C" size_t merlot_attention_bwd_workspace_bytes(int B, int S, int heads) {
+  const int parts = merlot_attention_bwd_dq_parts(S);
+  return (size_t)(parts > 0 ? parts : 1) * (size_t)B * S * heads * 64 * sizeof(float);
 }
 
 extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
@@ -723,6 +813,8 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
   AttnDev p; fill_dev(a, &p);
   const int H = p.H;
   const long long tokens = (long long)a->B * a->S;
+  const int parts = merlot_attention_bwd_dq_parts(a->S);
+  p.dq_part_stride = (size_t)tokens * a->ld_dq;
   {  // D = rowsum(dO * O)
     const long long threads = tokens * a->heads * 8;
     MB_CHECK_CUDA(launch_pdl(attn_dsum_kernel, dim3((unsigned)ceil_div_ll(threads, 256)), dim3(256), 0, stream,
@@ -730,27 +822,36 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
                              a->B, a->S, a->heads));
     MB_CHECK_LAUNCH();
   }
-  CUtensorMap tm, tdo;
-  rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)tokens, (uint64_t)a->ld_qkv, 64, 128);
+  CUtensorMap tkv, tq, tdo;
+  rc = make_tmap_bf16_2d(&tkv, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)tokens, (uint64_t)a->ld_qkv, 64, 128);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tdo, a->d_ctx, (uint64_t)a->ld_ctx, (uint64_t)tokens, (uint64_t)a->ld_ctx, 64, 128);
+  rc = make_tmap_bf16_2d(&tq, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)tokens, (uint64_t)a->ld_qkv, 64, BQ);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tdo, a->d_ctx, (uint64_t)a->ld_ctx, (uint64_t)tokens, (uint64_t)a->ld_ctx, 64, BQ);
   if (rc) return rc;
   MB_REQUIRE(a->S <= MAX_MASK_WORDS * 32 - AT_M, MERLOT_ESHAPE, "attention_bwd: sequence longer than %d keys", MAX_MASK_WORDS * 32 - AT_M);
   static bool attr = false;
   if (!attr) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr = true;
   }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), BWD_SMEM, stream, tm, tdo, p));
-  else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), BWD_SMEM, stream, tm, tdo, p));
+  if (parts > 0) {
+    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, false>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, false>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+  } else {
+    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+  }
   MB_CHECK_LAUNCH();
   {
     long long slabs = ceil_div_ll(tokens, 64);
     if (slabs > 128) slabs = 128;
     MB_CHECK_CUDA(launch_pdl(attn_dqkv_finish_kernel, dim3(ceil_div(3 * H, 256), (unsigned)slabs), dim3(256), 0, stream, a->dq_accum,
-                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv));
+                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv, parts, p.dq_part_stride));
     MB_CHECK_LAUNCH();
   }
   return MERLOT_OK;
@@ -804,10 +905,16 @@ extern "C" int merlot_attention_colsum(const merlot_attn_t* a, void* stream_) {
   CUtensorMap tm;
   rc = make_tmap_bf16_2d(&tm, a->qkv, (uint64_t)a->ld_qkv, (uint64_t)a->B * a->S, (uint64_t)a->ld_qkv, 64, 128);
   if (rc) return rc;
+  MB_REQUIRE(a->S <= MAX_MASK_WORDS * 32 - AT_M, MERLOT_ESHAPE, "attention_colsum: sequence longer than %d keys", MAX_MASK_WORDS * 32 - AT_M);
   static bool attr = false;
-  if (!attr) { MB_CHECK_CUDA(cudaFuncSetAttribute(attn_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM)); attr = true; }
+  if (!attr) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_colsum_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_colsum_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+    attr = true;
+  }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
-  MB_CHECK_CUDA(launch_pdl(attn_colsum_kernel, grid, dim3(128), CS_SMEM, stream, tm, p));
+  if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_colsum_kernel<true>, grid, dim3(128), CS_SMEM, stream, tm, p));
+  else MB_CHECK_CUDA(launch_pdl(attn_colsum_kernel<false>, grid, dim3(128), CS_SMEM, stream, tm, p));
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }

@@ -114,7 +114,8 @@ extern "C" size_t merlot_stack_activation_bytes(const merlot_stack_t* s) {
 extern "C" size_t merlot_stack_scratch_bytes(const merlot_stack_t* s) {
   if (!s) return 0;
   const size_t M = (size_t)s->B * s->S, H = s->H, I = s->I;
-  return align_up(M * H * 2) * 4 + align_up(M * 3 * H * 2) + align_up(M * I * 2) + align_up(M * H * 4) +
+  return align_up(M * H * 2) * 4 + align_up(M * 3 * H * 2) + align_up(M * I * 2) +
+         align_up(merlot_attention_bwd_workspace_bytes(s->B, s->S, s->heads)) +
          align_up((size_t)s->B * s->heads * s->S * 4) + align_up(merlot_layernorm_bwd_workspace_bytes(s->H));
 }
 
@@ -201,10 +202,11 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
   char* dmask = take((size_t)M * H * 2);  // dropout-masked copy of the stream gradient
   char* dqkv = take((size_t)M * 3 * H * 2);
   char* dpre = take((size_t)M * I * 2);
-  float* dq_acc = (float*)take((size_t)M * H * 4);
+  float* dq_acc = (float*)take(merlot_attention_bwd_workspace_bytes(s->B, s->S, s->heads));
   float* dsum = (float*)take((size_t)s->B * s->heads * s->S * 4);
   void* lnws = take(merlot_layernorm_bwd_workspace_bytes(H));
-  MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)M * H * 4, st));
+  if (merlot_attention_bwd_dq_parts(s->S) == 0)  // atomic mode: the single slice must start at zero (K3 hands it back zeroed)
+    MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)M * H * 4, st));
 
   const bool drop = s->hidden_dropout_p > 0.f;
   // ln_bwd(dy, x, stats, gamma, dres) -> dx [+ dropout-masked copy + bias gradient of the linear layer that fed this
@@ -217,13 +219,19 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
   };
   char* dh = dhA;
   char* dh_other = dhB;
+  // partial backward (bwd_lo/bwd_hi): the stream gradient is back in dhA after every complete layer (two swaps per layer), so
+  // a call that resumes below the top layer simply continues from dhA
+  const int l_hi = (s->bwd_hi > 0) ? s->bwd_hi : s->layers;
+  const int l_lo = (s->bwd_hi > 0) ? s->bwd_lo : 0;
+  MB_REQUIRE(0 <= l_lo && l_lo < l_hi && l_hi <= s->layers, MERLOT_EINVAL, "stack_backward: bad layer range [%d, %d)", l_lo, l_hi);
+  if (l_hi == s->layers)
   {  // final LN; its output is the gradient of the last layer's FFN2 output
     LayerAct A = carve(s, arena + per * (s->layers - 1));
     const merlot_layer_params_t& PL = s->layer_params[s->layers - 1];
     RC(ln_bwd_f(s->dy, A.hout, mean_f, rstd_f, s->final_gamma, nullptr, dh, s->d_final_gamma, s->d_final_beta, PL.g_b_2,
                 s->dropout_site_base + 2 * (s->layers - 1) + 1));
   }
-  for (int l = s->layers - 1; l >= 0; --l) {
+  for (int l = l_hi - 1; l >= l_lo; --l) {
     const merlot_layer_params_t& P = s->layer_params[l];
     LayerAct A = carve(s, arena + per * l);
     const void* h_in = (l == 0) ? s->h_in : (const void*)carve(s, arena + per * (l - 1)).hout;

@@ -117,11 +117,23 @@ class _Stack:
         L.check(L.lib().merlot_stack_forward(C.byref(self.d), ops._stream()))
         return self.y
 
-    def backward(self, dy, dh_in):
+    def backward(self, dy, dh_in, layer_groups=None, on_group_done=None):
+        """layer_groups = [(lo, hi), ...] top-down (hi of the first = layers, lo of the last = 0): one C call per group, with
+        on_group_done(k) in between -- the parameter gradients of group k are final when its kernels have run."""
         d = self.d
         scratch = self.bufs.get(f"{self.tag}.scratch", (L.lib().merlot_stack_scratch_bytes(C.byref(d)),), torch.uint8)
         d.dy, d.dh_in, d.scratch = dy.data_ptr(), dh_in.data_ptr(), scratch.data_ptr()
-        L.check(L.lib().merlot_stack_backward(C.byref(d), ops._stream()))
+        if not layer_groups:
+            d.bwd_lo, d.bwd_hi = 0, 0
+            L.check(L.lib().merlot_stack_backward(C.byref(d), ops._stream()))
+            return dh_in
+        assert layer_groups[0][1] == d.layers and layer_groups[-1][0] == 0
+        for k, (lo, hi) in enumerate(layer_groups):
+            d.bwd_lo, d.bwd_hi = lo, hi
+            L.check(L.lib().merlot_stack_backward(C.byref(d), ops._stream()))
+            if on_group_done is not None:
+                on_group_done(k)
+        d.bwd_lo, d.bwd_hi = 0, 0
         return dh_in
 
 
@@ -942,7 +954,7 @@ class MerlotModel(object):
     # ---------------------------------------------------------------------------------------------------------
     # backward of the whole model: call after mask_loss / contrastive_loss / temporal_loss (whichever are in the loss)
     # ---------------------------------------------------------------------------------------------------------
-    def backward(self, on_non_vit_grads_ready=None):
+    def backward(self, on_non_vit_grads_ready=None, vit_layer_groups=None, on_vit_group_done=None):
         """d(lang_loss + contr_loss + temp_loss)/d(params) accumulated into store.g  (model/modeling.py:713 loss,
         utils/optimization.py:176 tf.gradients).  Order: heads -> joint encoder -> language-only encoder -> (callback: every
         gradient outside vision_backbone/vision_transformer is final; data-parallel training starts their all-reduce here)
@@ -1002,7 +1014,7 @@ class MerlotModel(object):
             on_non_vit_grads_ready()
         # ---- ViT ----
         d_h0v = bf.get("bwd.d_h0v", (Mv, H), torch.bfloat16)
-        self._vit.backward(d_hv, d_h0v)
+        self._vit.backward(d_hv, d_h0v, vit_layer_groups, on_vit_group_done)
         dxv = bf.get("bwd.dxsum_v", (Mv, H), torch.float32)
         ops.layernorm_bwd(d_h0v, bf.get("vit.xsum", (Mv, H), torch.float32), bf.get("vit.mean0", (Mv,), torch.float32),
                           bf.get("vit.rstd0", (Mv,), torch.float32), st.P(f"{vt}/LayerNorm_ctx_patches_pre_ln/gamma"), dxv,

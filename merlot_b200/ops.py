@@ -113,21 +113,31 @@ def attention_fwd(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional
     return ctx, lse
 
 
+def attention_bwd_workspace(B: int, S: int, heads: int, device) -> torch.Tensor:
+    """Zeroed fp32 dQ workspace of merlot_attention_bwd_workspace_bytes(B, S, heads) as [parts*B*S, H]."""
+    H = heads * 64
+    n = L.lib().merlot_attention_bwd_workspace_bytes(B, S, heads) // 4
+    return torch.zeros((n // H, H), dtype=torch.float32, device=device)
+
+
 def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_accum=None, dsum=None):
-    """K3: dqkv[B*S,3H] from d_ctx.  dq_accum must be zero on entry (it is returned zeroed)."""
+    """K3: dqkv[B*S,3H] from d_ctx.  dq_accum: fp32 workspace of merlot_attention_bwd_workspace_bytes (see the header);
+    in atomic mode (long sequences) it must be zero on entry and is returned zeroed."""
     a = _attn_desc(qkv, B, S, heads, valid)
     H = heads * a.head_dim
     dev = qkv.device
     if dqkv is None:
         dqkv = torch.empty((B * S, 3 * H), dtype=torch.bfloat16, device=dev)
+    need = L.lib().merlot_attention_bwd_workspace_bytes(B, S, heads) // 4
     if dq_accum is None:
-        dq_accum = torch.zeros((B * S, H), dtype=torch.float32, device=dev)
+        dq_accum = torch.zeros((need // H, H), dtype=torch.float32, device=dev)
+    assert dq_accum.numel() >= need, "dq_accum smaller than merlot_attention_bwd_workspace_bytes"
     if dsum is None:
         dsum = torch.empty((B, heads, S), dtype=torch.float32, device=dev)
     a.ctx, a.ld_ctx, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
     assert d_ctx.stride(0) == ctx.stride(0)
     a.d_ctx, a.dsum = d_ctx.data_ptr(), dsum.data_ptr()
-    a.dq_accum, a.ld_dq = dq_accum.data_ptr(), dq_accum.stride(0)
+    a.dq_accum, a.ld_dq = dq_accum.data_ptr(), H
     a.dqkv, a.ld_dqkv = dqkv.data_ptr(), dqkv.stride(0)
     L.check(L.lib().merlot_attention_bwd(C.byref(a), _stream()))
     return dqkv

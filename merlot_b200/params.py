@@ -227,6 +227,38 @@ class ParamStore:
             self.v = torch.zeros(off, dtype=torch.bfloat16, device=self.device)
         self.global_step = 0
 
+    def vit_buckets(self, n_groups: int = 4):
+        """Gradient buckets of the ViT for the data-parallel all-reduce, in BACKWARD order.  Returns (layer_groups, ranges):
+        layer_groups[k] = (lo, hi) layers walked by the k-th partial stack backward (top-down); ranges[k] = arena ranges whose
+        gradients are final once group k has run.  The weight-decayed kernels of a layer group are contiguous in the arena;
+        everything else of the ViT (patch/stem kernels, position tables, every LayerNorm and bias) rides in the last bucket."""
+        vt = "vision_backbone/vision_transformer/"
+        layers = self.cfg.get("num_vision_transformer_hidden_layers", self.cfg["num_hidden_layers"])
+        n_groups = max(1, min(n_groups, layers))
+        cuts = [round(layers * k / n_groups) for k in range(n_groups + 1)]
+        groups = [(cuts[k], cuts[k + 1]) for k in range(n_groups)][::-1]
+        ranges, taken = [], []
+        for lo, hi in groups[:-1]:
+            es = [e for e in self.entries.values() if e.name.startswith(vt + "layer") and e.name.endswith("/kernel")
+                  and lo <= int(e.name[len(vt) + 5:len(vt) + 7]) < hi]
+            a, b = min(e.offset for e in es), max(e.offset + e.padded for e in es)
+            assert sum(e.padded for e in es) == b - a, "ViT layer kernels are not contiguous in the arena"
+            ranges.append([(a, b)])
+            taken.append((a, b))
+        last = []
+        for a, b in self.vit_ranges:  # whatever the earlier buckets left
+            cur = a
+            for ta, tb in sorted(taken):
+                if tb <= cur or ta >= b:
+                    continue
+                if ta > cur:
+                    last.append((cur, ta))
+                cur = max(cur, tb)
+            if cur < b:
+                last.append((cur, b))
+        ranges.append(last)
+        return groups, ranges
+
     # ---- views ----
     def _view(self, buf: torch.Tensor, name: str) -> torch.Tensor:
         e = self.entries[name]

@@ -105,7 +105,7 @@ class StepSpec:
 
 
 def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, dist: Optional[DataParallel] = None,
-                     device="cuda", seed: int = 0, log_attention_probs: bool = True):
+                     device="cuda", seed: int = 0, log_attention_probs: bool = True, vit_grad_buckets: int = 4):
     """model/modeling.py:671-810.  `seed` is the run seed of every random draw of the step (dropout masks, Gumbel noise,
     span lengths, 10/80/10 options, replacement ids): replica r at step t uses seed + t*world + r, so replicas draw
     independently like the reference's per-core tf.random ops and two runs with different seeds differ.
@@ -153,14 +153,26 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
                     dist.all_reduce_grads(store.g)
                 optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True)
             elif world > 1:
-                # bucket 1 (everything outside the ViT) is all-reduced while the ViT backward runs; bucket 2 (ViT) is
-                # all-reduced while AdamW updates bucket 1
-                model.backward(on_non_vit_grads_ready=lambda: pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges)))
-                vit_pending = dist.all_reduce_ranges_async(store.g, store.vit_ranges)
+                # Bucketed, overlapped gradient all-reduce (CrossShardOptimizer's mean, utils/optimization.py:241-245; the 1/world
+                # is folded into AdamW).  Bucket 0 = everything outside the ViT, reduced while the ViT backward runs; the ViT is
+                # walked in layer groups top-down and each group's kernels are reduced as soon as that group has run, so only
+                # the last group's bucket is exposed.  AdamW updates every bucket as its reduction lands.
+                groups, vit_ranges = store.vit_buckets(vit_grad_buckets)
+                vit_pending = []
+
+                def on_group(k):
+                    if k + 1 < len(groups):
+                        vit_pending.append(dist.all_reduce_ranges_async(store.g, vit_ranges[k]))
+
+                model.backward(on_non_vit_grads_ready=lambda: pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges)),
+                               vit_layer_groups=groups, on_vit_group_done=on_group)
+                vit_pending.append(dist.all_reduce_ranges_async(store.g, vit_ranges[-1]))
                 dist.wait_all(pending)
                 optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=store.rest_ranges, advance=False)
-                dist.wait_all(vit_pending)
-                optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=store.vit_ranges, advance=True)
+                for k, hs in enumerate(vit_pending):
+                    dist.wait_all(hs)
+                    optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=vit_ranges[k],
+                                              advance=(k + 1 == len(vit_pending)))
             else:
                 model.backward()
                 optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True)

@@ -215,7 +215,7 @@ def test_cfg5_attention_S3608(masked):
     rep["colsum_rel"] = rel(colsum.reshape(B, S), probs.detach().mean(1).sum(1))
     octx.permute(0, 2, 1, 3).backward(dctx.float().reshape(B, S, heads, 64))
     dqkv = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=DEV)
-    dq_acc = torch.zeros(B * S, H, dtype=torch.float32, device=DEV)
+    dq_acc = ops.attention_bwd_workspace(B, S, heads, DEV)
     dsum = torch.empty(B, heads, S, dtype=torch.float32, device=DEV)
     ops.attention_bwd(qkv_d, ctx, dctx_d, lse, B, S, heads, dqkv=dqkv, dq_accum=dq_acc, dsum=dsum, valid=vd)
     d3 = dqkv.float().cpu().reshape(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)

@@ -171,8 +171,8 @@ def test_attention_fwd_bwd_colsum(ops, B, S, heads, masked):
     ctx, lse = ops.attention_fwd(qkv.to(DEV), B, S, heads, vd)
     assert rel(ctx, ctx_ref) < 1e-2
     d_ctx = (torch.randn(B * S, H, generator=g) * 0.1).bfloat16()
-    if valid is not None:
-        d_ctx = d_ctx * valid[:, None].to(d_ctx.dtype)  # padding rows never receive gradient in the model
+    # padding QUERY rows get a gradient too (they never do in the model): the reference's scores*m - 1e10*(1-m) keeps their
+    # uniform probabilities in dV and sends nothing into q / k (utils/transformer.py:109-112)
     dqkv = ops.attention_bwd(qkv.to(DEV), ctx, d_ctx.to(DEV), lse, B, S, heads, vd)
     ctx_ref.backward(d_ctx.float())
     ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)

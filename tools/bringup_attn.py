@@ -69,7 +69,7 @@ def perf():
         qkv = torch.randn(B * S, 3 * H, device=dev).bfloat16()
         ctx, lse = ops.attention_fwd(qkv, B, S, heads)
         d_ctx = torch.randn_like(ctx)
-        dq_acc = torch.zeros(B * S, H, device=dev)
+        dq_acc = ops.attention_bwd_workspace(B, S, heads, dev)
         dqkv = torch.empty_like(qkv)
         for name, fn, mult in (("fwd", lambda: ops.attention_fwd(qkv, B, S, heads, ctx=ctx, lse=lse), 1.0),
                                ("bwd", lambda: ops.attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, dqkv=dqkv,

@@ -58,7 +58,7 @@ qkv = bf(B * S, 3 * H)
 ctx, lse = ops.attention_fwd(qkv, B, S, heads)
 dctx = bf(B * S, H)
 dqkv = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=dev)
-dq_acc = torch.zeros(B * S, H, dtype=torch.float32, device=dev)
+dq_acc = ops.attention_bwd_workspace(B, S, heads, dev)
 dsum = torch.empty(B, heads, S, dtype=torch.float32, device=dev)
 colsum = torch.zeros(B * S, dtype=torch.float32, device=dev)
 NP = 85_000_000  # one 12-layer stack's worth of parameters
