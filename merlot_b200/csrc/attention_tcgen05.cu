@@ -37,6 +37,25 @@ struct AttnDev {
   float* colsum2;                // optional: queries >= colsum_split accumulate here instead
   int colsum_split;              // 0 = no split
   int colsum_valid_q;            // 1 = only valid (non-padding) queries contribute (attention_log, modeling.py:192-193)
+  unsigned long long* dbg;       // optional phase counters (merlot_attention_debug_counters): [0,8) forward, [8,16) backward
+};
+
+// phase timing of ONE softmax thread per CTA (cycles summed over all CTAs; tools/attn_phases.py prints per-tile averages)
+struct PhaseClock {
+  long long t, acc[8];
+  bool on;
+  __device__ __forceinline__ PhaseClock(bool enabled) : on(enabled) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0;
+    t = on ? clock64() : 0;
+  }
+  __device__ __forceinline__ void lap(int phase) {
+    if (on) { const long long n = clock64(); acc[phase] += n - t; t = n; }
+  }
+  __device__ __forceinline__ void flush(unsigned long long* dst) {
+    if (on)
+      for (int i = 0; i < 8; ++i) atomicAdd(dst + i, (unsigned long long)acc[i]);
+  }
 };
 
 // score in the log2 domain: sc2 = scale * log2(e)
@@ -81,6 +100,9 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // tcgen05.mma / TMA are issued by ONE thread; the predicate must come from elect.sync (and every operand must be provably
+  // warp-uniform), otherwise ptxas wraps each instruction in a per-lane ELECT / BRA.U.ANY loop that costs ~100 cycles per MMA
+  const bool leader = elect_one(), warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;
   const int q0 = blockIdx.x * AT_M, h = blockIdx.y, b = blockIdx.z;
   pdl_launch_dependents();
   const int S = p.S, H = p.H;
@@ -104,11 +126,11 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // provably warp-uniform: no per-lane waterfall around tcgen05.mma
   const uint32_t tS = tmem, tO = tmem + 64;
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
-  if (tid == 0) {
+  if (warp0) if (leader) {
     mbar_arrive_expect_tx(bar_q, 16384);
     tma_load_2d(sQ, &tm_q, bar_q, h * AT_D, tok0 + q0);
     mbar_arrive_expect_tx(bar_k, 8192);
@@ -137,20 +159,22 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
     for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tS, desc_kmajor(qa, k), desc_kmajor(ka, k), idesc_s, k > 0);
     umma_commit(bar_s);
   };
-  if (tid == 0) {
+  if (warp0) if (leader) {
     mbar_wait(bar_q, 0);
     issue_s(0);
   }
 
   // Per key tile the threads wait ONCE, for { P V of tile j-1, S of tile j } (S_j is issued right behind P V_{j-1}, so the
   // tensor pipe runs them back to back); K_{j+1} and V_{j+1} are fetched while the softmax of tile j runs.
+  PhaseClock pc(p.dbg != nullptr && tid == 32);
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
     const int k0 = j * FK;
     const int nu = nu_of(j);
     mbar_wait(bar_s, ph);
     tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // S_j and P V_{j-1} have completed: the K tile and V buffer (j+1)&1 are free
+    pc.lap(0);
+    if (warp0) if (leader && j + 1 < n_kv) {  // S_j and P V_{j-1} have completed: the K tile and V buffer (j+1)&1 are free
       mbar_arrive_expect_tx(bar_k, 8192);
       tma_load_2d(sK, &tm_kv, bar_k, H + h * AT_D, tok0 + (j + 1) * FK);
       mbar_arrive_expect_tx(&bar_v[(j + 1) & 1], 8192);
@@ -186,6 +210,7 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
         }
       }
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      pc.lap(1);
       // ---- lazy running max: advance (and correct O in TMEM) only when the row max grew by more than 2^8 ----
       const bool need = mx > m_used + 8.0f;  // always true on the first tile (m_used = -inf)
       if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -203,6 +228,7 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
         l_run *= f;
       }
       if (need) m_used = mx;
+      pc.lap(2);
       // ---- p = 2^(x - m), P (bf16) into the K-major swizzled A tile ----
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -222,10 +248,12 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
       }
       l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
     }
+    pc.lap(3);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    pc.lap(4);
+    if (warp0) if (leader) {
       tc_fence_after();
       mbar_wait(&bar_v[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
@@ -241,6 +269,8 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
   }
   mbar_wait(bar_o, 0);  // last P V: O is final
   tc_fence_after();
+  pc.lap(5);
+  pc.acc[6] = n_kv;
 
   if (warp_live) {
     const float inv = 1.0f / l_run;
@@ -263,6 +293,8 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
     }
     if (q_in && p.lse) p.lse[((size_t)b * p.heads + h) * S + q] = (m_used + log2f(l_run)) * LN2;
   }
+  pc.lap(7);
+  pc.flush(p.dbg);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
@@ -304,6 +336,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
   // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every chunk's columns
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2, quad = warp & 3, row_t = quad * 32 + lane;
+  const bool leader = elect_one(), warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // see attn_fwd_kernel
   pdl_launch_dependents();
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
@@ -345,7 +378,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // provably warp-uniform: no per-lane waterfall around tcgen05.mma
   const uint32_t tST = tmem, tdPT = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tdQ = tmem;  // dQ reuses the S^T columns
   const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
@@ -372,7 +405,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     umma_commit(bar_1);
   };
 
-  if (tid == 0) {
+  if (warp0) if (leader) {
     mbar_arrive_expect_tx(bar_kv, 32768);
     tma_load_2d(sK, &tm_kv, bar_kv, H + h * AT_D, tok0 + k0);
     tma_load_2d(sV, &tm_kv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
@@ -387,6 +420,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
   const float sc2 = p.scale * LOG2E;
   float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)blockIdx.x * p.dq_part_stride);
 
+  PhaseClock pc(p.dbg != nullptr && tid == 32);
   for (int i = 0; i < n_q; ++i) {
     const uint32_t ph = i & 1;
     const int q0 = i * BQ;
@@ -395,6 +429,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     const int nu = nu_of(i);
     mbar_wait(bar_1, ph);
     tc_fence_after();
+    pc.lap(0);
     if (!warp_dead) {
 #pragma unroll 1
       for (int u = wg * 2; u < wg * 2 + 2; ++u) {
@@ -441,11 +476,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         }
       }
     }
+    pc.lap(1);
     if (i + 1 < n_q) stage_stats(i + 1);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    pc.lap(2);
+    if (warp0) if (leader) {
       tc_fence_after();
       const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQd + (i & 1) * 16384), da = qa + 8192,
                      ka = smem_u32(sK);
@@ -462,7 +499,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
     }
     mbar_wait(bar_2, ph);
     tc_fence_after();
-    if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
+    pc.lap(3);
+    if (warp0) if (leader && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
     {  // dQ partial of this key tile: M = 64 accumulator, row 16*quad + l lives on lane 32*quad + l (l < 16)
       const int q = q0 + quad * 16 + lane;
       uint32_t r[32];
@@ -484,10 +522,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
         }
       }
     }
+    pc.lap(4);
     tc_fence_before();
     __syncthreads();  // dQ TMEM (= S^T columns) / P^T, dS^T smem are reused by the next chunk
-    if (tid == 0 && i + 1 < n_q) { tc_fence_after(); issue_st(i + 1); }
+    pc.lap(5);
+    if (warp0) if (leader && i + 1 < n_q) { tc_fence_after(); issue_st(i + 1); }
   }
+  pc.acc[6] = n_q;
   // ---- dK, dV for this key tile (exclusive rows) ----
   tc_fence_after();
 #pragma unroll
@@ -511,6 +552,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       }
     }
   }
+  pc.lap(7);
+  pc.flush(p.dbg ? p.dbg + 8 : nullptr);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
@@ -628,6 +671,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   uint64_t *bar_k = bars, *bar_q = bars + 1 /* [2] */, *bar_s = bars + 3 /* [2] */;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool leader = elect_one(), warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // see attn_fwd_kernel
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H, tok0 = b * S;
   const int n_q = (S + AT_M - 1) / AT_M;
@@ -654,7 +698,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_ptr;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // provably warp-uniform: no per-lane waterfall around tcgen05.mma
   const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
   auto load_q = [&](int i) {
     mbar_arrive_expect_tx(&bar_q[i & 1], 16384);
@@ -670,7 +714,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
     for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tmem + (i & 1) * 128, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc, k > 0);
     umma_commit(&bar_s[i & 1]);
   };
-  if (tid == 0) {
+  if (warp0) if (leader) {
     mbar_arrive_expect_tx(bar_k, 16384);
     tma_load_2d(sK, &tm_qkv, bar_k, H + h * AT_D, tok0 + k0);
     load_q(0);
@@ -687,11 +731,11 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   const int split = p.colsum2 ? p.colsum_split : 0x7fffffff;
   for (int i = 0; i < n_q; ++i) {
     const int q0 = i * AT_M;
-    if (tid == 0 && i + 1 < n_q) issue(i + 1);   // runs under the exponentials below
+    if (warp0) if (leader && i + 1 < n_q) issue(i + 1);   // runs under the exponentials below
     if (i + 1 < n_q) stage_lse(i + 1);
     mbar_wait(&bar_s[i & 1], (uint32_t)((i >> 1) & 1));
     tc_fence_after();
-    if (tid == 0 && i + 2 < n_q) load_q(i + 2);  // S^T_i has consumed Q buffer i & 1
+    if (warp0) if (leader && i + 2 < n_q) load_q(i + 2);  // S^T_i has consumed Q buffer i & 1
     const float* nl = s_nlse + (i & 1) * AT_M;
     const int ncq = ncq_of(i);
     if (warp_live) {
@@ -737,6 +781,8 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
+static unsigned long long* g_attn_dbg = nullptr;  // merlot_attention_debug_counters
+
 static int check_common(const merlot_attn_t* a) {
   MB_REQUIRE(a != nullptr, MERLOT_EINVAL, "attention: null descriptor");
   MB_REQUIRE(a->B > 0 && a->S > 0 && a->heads > 0, MERLOT_ESHAPE, "attention: bad dims B=%d S=%d heads=%d", a->B, a->S,
@@ -761,11 +807,14 @@ static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
   p->colsum2 = a->colsum2;
   p->colsum_split = a->colsum_split;
   p->colsum_valid_q = a->colsum_valid_q;
+  p->dbg = g_attn_dbg;
 }
 
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" void merlot_attention_debug_counters(void* buf_u64x16) { g_attn_dbg = reinterpret_cast<unsigned long long*>(buf_u64x16); }
 
 extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

@@ -89,8 +89,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
   float* bias_slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform (see gemm_kernel.cuh)
   const int lane = threadIdx.x & 31;
+  const bool elected = elect_one();                                        // the single issuing lane of a warp
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   pdl_launch_dependents();
@@ -115,7 +116,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   pdl_wait();
 
   const int m2_blocks = (p.M + 255) / 256;  // pair tiles along M
@@ -125,7 +126,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elected) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -161,7 +162,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    if (leader) if (elected) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;

@@ -27,8 +27,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* bias_slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle = provably warp-uniform, single issuing lane through elect.sync, TMEM base through a shuffle:
+  // with anything less ptxas wraps every tcgen05.mma / TMA instruction in a per-lane ELECT / BRA.U.ANY loop (measured with
+  // tools/micro/mma_bench*.cu: 119 -> 32..128 cycles per MMA, i.e. the 128 x 256 x 16 MMA ran at 167 instead of 128 cycles)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const bool leader = elect_one();
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
@@ -51,14 +55,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (leader) {
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
@@ -97,7 +101,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
