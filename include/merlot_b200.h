@@ -117,10 +117,12 @@ typedef struct merlot_attn {
 
 int merlot_attention_fwd(const merlot_attn_t* a, void* stream);
 int merlot_attention_bwd(const merlot_attn_t* a, void* stream);
-/* diagnostics: 16 x u64 device buffer (or NULL = off); one softmax thread per CTA adds its per-phase cycle counts, [0,8) = K2
+/* diagnostics: 24 x u64 device buffer (or NULL = off; [16,24) = the K3 issuer lane); one softmax thread per CTA adds its per-phase cycle counts, [0,8) = K2
  * {wait S, load+max, rescale, exp+store P, fence+sync, final wait, key tiles, epilogue}, [8,16) = K3 {wait S^T/dP^T, softmax
  * arithmetic, fence+sync, wait dV/dK/dQ, dQ read-out, sync, query chunks, dK/dV epilogue} (tools/attn_phases.py) */
-void merlot_attention_debug_counters(void* buf_u64x16);
+void merlot_attention_debug_counters(void* buf_u64x24);
+/* timing experiments (results are WRONG when non-zero): K3 bit 0 = skip the arithmetic, bit 1 = skip MMA2, bit 2 = skip MMA1 */
+void merlot_attention_debug_mode(int mode);
 int merlot_attention_bwd_dq_parts(int S);                          /* slices used by bwd for this S; 0 = atomic single slice */
 size_t merlot_attention_bwd_workspace_bytes(int B, int S, int heads); /* bytes of dq_accum (ld_dq = heads*64) */
 int merlot_attention_colsum(const merlot_attn_t* a, void* stream);

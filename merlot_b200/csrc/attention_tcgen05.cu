@@ -37,6 +37,7 @@ struct AttnDev {
   float* colsum2;                // optional: queries >= colsum_split accumulate here instead
   int colsum_split;              // 0 = no split
   int colsum_valid_q;            // 1 = only valid (non-padding) queries contribute (attention_log, modeling.py:192-193)
+  int dbg_mode;                  // timing experiments only (merlot_attention_debug_mode): 1 = no arithmetic, 2 = no MMA2, 4 = no MMA1
   unsigned long long* dbg;       // optional phase counters (merlot_attention_debug_counters): [0,8) forward, [8,16) backward
 };
 
@@ -301,42 +302,52 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// backward (v2): one CTA per (128-key tile, head, batch), TWO CTAs resident per SM (256 TMEM columns, ~100 KB smem each) so
-// that one CTA's tensor phase runs under the other's softmax phase.  Keys sit on the TMEM lanes; the queries are walked in
-// chunks of 64 (double-buffered Q/dO, prefetched by TMA):
-//   S^T = K Q^T, dP^T = V dO^T  ->  P^T, dS^T (bf16, swizzled smem)  ->  dV += P^T dO, dK += dS^T Q (TMEM, whole key tile),
-//   dQ_chunk = dS K  (M = 64 accumulator: rows 16w..16w+15 live on lanes 32w..32w+15, "half subpartition" layout).
+// backward (v3): warp-specialised, software-pipelined.  One CTA per (128-key tile, head, batch), 288 threads:
+//   warps 0-7  softmax / gradient arithmetic (two warps per TMEM lane quadrant; keys sit on the lanes),
+//   warp  8    issuer: TMA loads, every tcgen05.mma (one elected lane), per-chunk statistics staging (all 32 lanes).
+// The queries are walked in chunks of 64.  Per chunk i:
+//   MMA1(i):  S^T = K Q^T, dP^T = V dO^T                      -> TMEM buffers i & 1 (double-buffered: issued two chunks ahead)
+//   math(i):  P^T = exp2(S^T sc - lse), dS'^T = P^T (dP^T - D) -> bf16, 128B-swizzled smem buffers i & 1
+//   MMA2(i):  dV += P^T dO, dK += dS'^T Q (TMEM, whole key tile), dQ_chunk = dS' K (M = 64 accumulator, TMEM buffers i & 1)
+//   drain(i): dQ_chunk TMEM -> warp-private smem transposition -> coalesced fp32 stores
+// so the tensor pipe always has MMA2(i-1) / MMA1(i+1) queued while the arithmetic of chunk i runs; nothing in the loop is a
+// CTA-wide barrier (mbarriers between the issuer and the 8 arithmetic warps only).  1/sqrt(d) is applied once per output
+// (dK in the epilogue, dQ in attn_dqkv_finish) instead of once per score.
 // dQ never touches an atomic when the sequence has <= 4 key tiles: every CTA stores its partial for its key tile into its own
-// slice of the [parts][tokens][H] fp32 workspace (plain coalesced stores) and attn_dqkv_finish sums the slices; longer
+// slice of the [parts][tokens][H] fp32 workspace and attn_dqkv_finish sums the slices (bitwise reproducible); longer
 // sequences red.add into one slice.  Warps whose 32 keys all lie past the sequence end (ragged last key tile: S = 266 has 10
-// keys there) zero their P^T / dS^T rows once and skip the softmax arithmetic.
+// keys there) zero their P^T / dS^T rows once and skip the arithmetic.
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int BQ = 64;              // queries per chunk
 constexpr int MAX_DQ_PARTS = 4;     // key tiles per sequence for which dQ goes through per-tile slices instead of atomics
-constexpr int BWD_SMEM = 16384 * 2 + 2 * 16384 + 16384 * 2 + 1024 + 512 + 128 + 1024;
+constexpr int BWD_QSTAGES = 4;      // Q/dO chunk ring
+constexpr int BWD_THREADS = 288;
+constexpr int BWD_SMEM = 16384 * 2 + BWD_QSTAGES * 16384 + 2 * 16384 + 2 * 16384 + 8 * 2048 + 1024 + 512 + 256 + 1024;
 
 template <bool HAS_MASK, bool DQ_ATOMIC>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                 const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = smem + 16384;
-  uint8_t* sQd = smem + 32768;            // 2 x { Q chunk 8 KB, dO chunk 8 KB }
-  uint8_t* sPT = smem + 32768 + 32768;    // P^T  [128 keys][64 q] bf16: one 128B-swizzled atom
-  uint8_t* sdST = sPT + 16384;            // dS^T same layout
-  float* s_nlse = reinterpret_cast<float*>(sdST + 16384);  // [2][64]  -lse * log2(e)
-  float* s_dsum = s_nlse + 128;                            // [2][64]
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 128);  // [MAX_MASK_WORDS]
+  uint8_t* sQd = smem + 32768;                               // BWD_QSTAGES x { Q chunk 8 KB, dO chunk 8 KB }
+  uint8_t* sPT = sQd + BWD_QSTAGES * 16384;                  // [2] P^T  [128 keys][64 q] bf16: one 128B-swizzled atom each
+  uint8_t* sdST = sPT + 2 * 16384;                           // [2] dS^T same layout
+  uint8_t* sStg = sdST + 2 * 16384;                          // 8 warp-private 2 KB transposition slots
+  float* s_nlse = reinterpret_cast<float*>(sStg + 8 * 2048);  // [2][64]  -lse * log2(e)
+  float* s_dsum = s_nlse + 128;                              // [2][64]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 128);  // [MAX_MASK_WORDS] query validity bits
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_mask) + 512);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [2] */, *bar_1 = bars + 3, *bar_2 = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [4] */, *bar_s = bars + 5 /* [2] */, *bar_st = bars + 7 /* [2] */, *bar_p = bars + 9 /* [2] */,
+           *bar_d = bars + 11 /* [2] */;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
-  // 256 threads: two warps per TMEM lane quadrant; warp-group `wg` owns half of every chunk's columns
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, quad = warp & 3, row_t = quad * 32 + lane;
-  const bool leader = elect_one(), warp0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // see attn_fwd_kernel
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (see attn_fwd_kernel)
+  const bool leader = elect_one();
+  const int wg = (warp >> 2) & 1, quad = warp & 3, row_t = quad * 32 + lane;
   pdl_launch_dependents();
   const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
@@ -345,218 +356,303 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do);
-    mbar_init(bar_kv, 1); mbar_init(&bar_q[0], 1); mbar_init(&bar_q[1], 1); mbar_init(bar_1, 1); mbar_init(bar_2, 1);
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < BWD_QSTAGES; ++i) mbar_init(&bar_q[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_st[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_d[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 0) { tmem_alloc(tmem_ptr, 256); tmem_relinquish(); }
-  // a warp whose 32 keys are all out of range contributes exact zeros: written once, arithmetic skipped afterwards
-  const bool warp_dead = (k0 + quad * 32) >= S;
+  if (warp == 8) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+  // a warp whose 32 keys are all out of range contributes exact zeros: written once (both buffers), arithmetic skipped afterwards
+  const bool warp_dead = warp < 8 && ((k0 + quad * 32) >= S || (p.dbg_mode & 1));
   if (warp_dead && wg == 0) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      *reinterpret_cast<uint4*>(sPT + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(sdST + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        *reinterpret_cast<uint4*>(sPT + bb * 16384 + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sdST + bb * 16384 + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
   pdl_wait();
-  if (HAS_MASK) {
+  if (HAS_MASK && warp < 8) {
     for (int k = tid; k < n_q * BQ; k += 256) {
       const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
       const uint32_t w = __ballot_sync(0xffffffffu, v);
       if (lane == 0) s_mask[k >> 5] = w;
     }
   }
-  auto stage_stats = [&](int i) {  // -lse*log2e and D of query chunk i -> smem buffer i&1
-    if (tid < BQ) {
-      const int q = i * BQ + tid;
-      const size_t o = ((size_t)b * p.heads + h) * S + q;
-      s_nlse[(i & 1) * BQ + tid] = (q < S) ? -p.lse[o] * LOG2E : 0.f;
-      s_dsum[(i & 1) * BQ + tid] = (q < S) ? p.dsum[o] : 0.f;
-    }
-  };
-  stage_stats(0);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // provably warp-uniform: no per-lane waterfall around tcgen05.mma
-  const uint32_t tST = tmem, tdPT = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tdQ = tmem;  // dQ reuses the S^T columns
-  const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-
-  // a ragged last chunk only costs its 16-query units (S^T / dP^T with N = 16 nu, nu softmax units, nu k16-steps of dV / dK)
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  // TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256, dK 320, dQ[2] 384/448
+  const uint32_t tdV = tmem + 256, tdK = tmem + 320;
+  // a ragged last chunk only costs its 16-query units (S^T / dP^T with N = 16 nu, nu arithmetic units, nu k16-steps of dV / dK)
   auto nu_of = [&](int i) { return min(BQ / 16, (S - i * BQ + 15) >> 4); };
-  constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
-  constexpr uint32_t idesc_dq = make_idesc_bf16(BQ, AT_D, 1, 1);     // M = 64: A = dS (MN-major view of dS^T), B = K MN-major
 
-  auto load_q = [&](int i) {
-    uint8_t* buf = sQd + (i & 1) * 16384;
-    mbar_arrive_expect_tx(&bar_q[i & 1], 16384);
-    tma_load_2d(buf, &tm_q, &bar_q[i & 1], h * AT_D, tok0 + i * BQ);
-    tma_load_2d(buf + 8192, &tm_do, &bar_q[i & 1], h * AT_D, tok0 + i * BQ);
-  };
-  auto issue_st = [&](int i) {  // S^T and dP^T of query chunk i
-    mbar_wait(&bar_q[i & 1], (uint32_t)((i >> 1) & 1));
-    tc_fence_after();
-    const uint32_t ka = smem_u32(sK), va = smem_u32(sV), qa = smem_u32(sQd + (i & 1) * 16384), da = qa + 8192;
-    const uint32_t idesc_st = make_idesc_bf16(AT_N, nu_of(i) * 16, 0, 0);  // S^T, dP^T : both operands K-major (d)
+  if (warp == 8) {
+    // ================================= issuer warp =================================
+    constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
+    constexpr uint32_t idesc_dq = make_idesc_bf16(BQ, AT_D, 1, 1);     // M = 64: A = dS (MN-major view of dS^T), B = K MN-major
+    const uint32_t ka = smem_u32(sK), va = smem_u32(sV);
+    auto load_q = [&](int i) {
+      if (leader) {
+        uint8_t* buf = sQd + (i & (BWD_QSTAGES - 1)) * 16384;
+        uint64_t* bq = &bar_q[i & (BWD_QSTAGES - 1)];
+        mbar_arrive_expect_tx(bq, 16384);
+        tma_load_2d(buf, &tm_q, bq, h * AT_D, tok0 + i * BQ);
+        tma_load_2d(buf + 8192, &tm_do, bq, h * AT_D, tok0 + i * BQ);
+      }
+    };
+    // -lse*log2e and D of query chunk i -> smem buffer i & 1 (all 32 lanes, 2 queries each).  The global loads are issued one
+    // loop iteration before the values are parked in smem, so their latency never sits in the issue path.
+    float st_nl[2], st_ds[2];
+    auto fetch_stats = [&](int i) {
+      const size_t o0 = ((size_t)b * p.heads + h) * S;
 #pragma unroll
-    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
+      for (int r = 0; r < 2; ++r) {
+        const int q = i * BQ + lane + r * 32;
+        st_nl[r] = (q < S) ? -p.lse[o0 + q] * LOG2E : 0.f;
+        st_ds[r] = (q < S) ? p.dsum[o0 + q] : 0.f;
+      }
+    };
+    auto put_stats = [&](int i) {
 #pragma unroll
-    for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
-    umma_commit(bar_1);
-  };
-
-  if (warp0) if (leader) {
-    mbar_arrive_expect_tx(bar_kv, 32768);
-    tma_load_2d(sK, &tm_kv, bar_kv, H + h * AT_D, tok0 + k0);
-    tma_load_2d(sV, &tm_kv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
-    load_q(0);
-    if (n_q > 1) load_q(1);
+      for (int r = 0; r < 2; ++r) {
+        s_nlse[(i & 1) * BQ + lane + r * 32] = st_nl[r];
+        s_dsum[(i & 1) * BQ + lane + r * 32] = st_ds[r];
+      }
+      __syncwarp();
+      if (leader) mbar_arrive(&bar_st[i & 1]);
+    };
+    auto issue_st = [&](int i) {  // MMA1: S^T and dP^T of query chunk i -> TMEM buffers i & 1
+      mbar_wait(&bar_q[i & (BWD_QSTAGES - 1)], (uint32_t)((i / BWD_QSTAGES) & 1));
+      tc_fence_after();
+      if (leader) {
+        const uint32_t qa = smem_u32(sQd + (i & (BWD_QSTAGES - 1)) * 16384), da = qa + 8192;
+        const uint32_t idesc_st = make_idesc_bf16(AT_N, nu_of(i) * 16, 0, 0);  // both operands K-major (d)
+        const uint32_t tST = tmem + (i & 1) * 64, tdPT = tmem + 128 + (i & 1) * 64;
+        if (!(p.dbg_mode & 4)) {
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
+        }
+        umma_commit(&bar_s[i & 1]);
+      }
+    };
+    if (leader) {
+      mbar_arrive_expect_tx(bar_kv, 32768);
+      tma_load_2d(sK, &tm_kv, bar_kv, H + h * AT_D, tok0 + k0);
+      tma_load_2d(sV, &tm_kv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
+    }
+    for (int i = 0; i < BWD_QSTAGES && i < n_q; ++i) load_q(i);
+    fetch_stats(0); put_stats(0);
+    if (n_q > 1) { fetch_stats(1); put_stats(1); }
+    if (n_q > 2) fetch_stats(2);
     mbar_wait(bar_kv, 0);
     issue_st(0);
-  }
-  const int kk = k0 + row_t;  // this thread's key row
-  const bool k_in = kk < S;
-  const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
-  const float sc2 = p.scale * LOG2E;
-  float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)blockIdx.x * p.dq_part_stride);
+    if (n_q > 1) issue_st(1);
+    PhaseClock ic(p.dbg != nullptr && leader);
+    for (int i = 0; i < n_q; ++i) {
+      const int bb = i & 1;
+      const int nu = nu_of(i);
+      mbar_wait(&bar_p[bb], (uint32_t)((i >> 1) & 1));  // P^T / dS^T of chunk i are in smem; its S^T / dP^T / statistics buffers
+      tc_fence_after();                                 // are free; dQ[bb] of chunk i-2 has been drained (program order per warp)
+      ic.lap(0);
+      if (leader) {
+        const uint32_t pa = smem_u32(sPT + bb * 16384), sa = smem_u32(sdST + bb * 16384);
+        const uint32_t qa = smem_u32(sQd + (i & (BWD_QSTAGES - 1)) * 16384), da = qa + 8192;
+        const uint32_t tdQ = tmem + 384 + bb * 64;
+        if (!(p.dbg_mode & 2)) {
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (contraction over q)
+          if (k < nu) umma_bf16_ss(tdV, desc_kmajor(pa, k), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
+          if (k < nu) umma_bf16_ss(tdK, desc_kmajor(sa, k), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < AT_N / 16; ++k)  // dQ_chunk = dS K  (contraction over the 128 keys; stale columns of a ragged chunk
+          umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 0), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);  // only feed rows that are never stored)
+        }
+        umma_commit(&bar_d[bb]);
+      }
+      ic.lap(1);
+      if (i + 2 < n_q) {
+        put_stats(i + 2);  // fetched during the previous iteration
+        if (i + 3 < n_q) fetch_stats(i + 3);
+        ic.lap(2);
+        issue_st(i + 2);
+        ic.lap(3);
+      }
+      if (i >= 1 && i + 3 < n_q) {  // refill the ring: the stage of chunk i-1 is free once MMA2(i-1) has read it
+        mbar_wait(&bar_d[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+        load_q(i + 3);
+      }
+      ic.lap(4);
+    }
+    ic.acc[6] = n_q;
+    ic.flush(p.dbg ? p.dbg + 16 : nullptr);
+  } else {
+    // ================================= arithmetic warps =================================
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int kk = k0 + row_t;  // this thread's key row
+    const bool k_in = kk < S;
+    const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
+    const float sc2 = p.scale * LOG2E;
+    float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)blockIdx.x * p.dq_part_stride);
+    uint8_t* slot = sStg + warp * 2048;  // [16 rows][128 B], 16-byte chunks XOR-swizzled by the row
+    PhaseClock pc(p.dbg != nullptr && tid == 32);
 
-  PhaseClock pc(p.dbg != nullptr && tid == 32);
-  for (int i = 0; i < n_q; ++i) {
-    const uint32_t ph = i & 1;
-    const int q0 = i * BQ;
-    const float* nlse = s_nlse + (i & 1) * BQ;
-    const float* dsm = s_dsum + (i & 1) * BQ;
-    const int nu = nu_of(i);
-    mbar_wait(bar_1, ph);
-    tc_fence_after();
-    pc.lap(0);
-    if (!warp_dead) {
-#pragma unroll 1
-      for (int u = wg * 2; u < wg * 2 + 2; ++u) {
-        if (u >= nu) break;  // warp-uniform
-        uint32_t rs[16], rd[16];
-        tmem_ld_32x16(tST + lane_off + u * 16, rs);
-        tmem_ld_32x16(tdPT + lane_off + u * 16, rd);
-        tmem_wait_ld();
-        const int qb = q0 + u * 16;
-        const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
-        const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
-        const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
-        uint32_t pk[8], dk[8];
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(nlse + u * 16 + e);
-          const float4 d4 = *reinterpret_cast<const float4*>(dsm + u * 16 + e);
-          const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pv[4], dv[4];
-#pragma unroll
-          for (int t4 = 0; t4 < 4; ++t4) {
-            float t = __uint_as_float(rs[e + t4]) * sc2;
-            if (!fast) {
-              t = vk ? t : MASKED_LOG2;
-              t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
-            }
-            float pr = ex2_approx(t + ls[t4]);
-            if (!fast) pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
-            pv[t4] = pr;
-            // d(score)/d(q k^T) = m * scale (utils/transformer.py:109-110: scores*m - 1e10*(1-m)): a padding QUERY row keeps its
-            // uniform probabilities for dV but sends nothing back into q and k
-            float g = pr * p.scale;
-            if (!fast) g = ((qw >> (e + t4)) & 1u) ? g : 0.f;
-            dv[t4] = (__uint_as_float(rd[e + t4]) - ds[t4]) * g;
-          }
-          pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-          dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
-        }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t off = sw128_offset(row_t, (uint32_t)(u * 2 + g));
-          *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-          *reinterpret_cast<uint4*>(sdST + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
-        }
-      }
-    }
-    pc.lap(1);
-    if (i + 1 < n_q) stage_stats(i + 1);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    pc.lap(2);
-    if (warp0) if (leader) {
+    // dQ partial of chunk j: M = 64 accumulator, row 16*quad + l lives on lane 32*quad + l (l < 16); this warp owns columns
+    // [32 wg, 32 wg + 32).  Transposed through the warp's slot so that every store instruction writes 4 full 128-byte lines.
+    auto drain = [&](int j) {
+      mbar_wait(&bar_d[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t pa = smem_u32(sPT), sa = smem_u32(sdST), qa = smem_u32(sQd + (i & 1) * 16384), da = qa + 8192,
-                     ka = smem_u32(sK);
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (contraction over q)
-        if (k < nu) umma_bf16_ss(tdV, desc_kmajor(pa, k), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
-#pragma unroll
-      for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
-        if (k < nu) umma_bf16_ss(tdK, desc_kmajor(sa, k), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
-#pragma unroll
-      for (int k = 0; k < AT_N / 16; ++k)  // dQ_chunk = dS K  (contraction over the 128 keys; stale columns of a ragged chunk
-        umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 0), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);  // only feed rows that are never stored)
-      umma_commit(bar_2);
-    }
-    mbar_wait(bar_2, ph);
-    tc_fence_after();
-    pc.lap(3);
-    if (warp0) if (leader && i + 2 < n_q) load_q(i + 2);  // buffer i&1 is free: every MMA that read it has completed
-    {  // dQ partial of this key tile: M = 64 accumulator, row 16*quad + l lives on lane 32*quad + l (l < 16)
-      const int q = q0 + quad * 16 + lane;
-      uint32_t r[32];
-      tmem_ld_32x32(tdQ + lane_off + wg * 32, r);
+      pc.lap(3);
+      // 16x256b: only the 16 live lanes of the M = 64 accumulator are read; thread t holds rows t/4 and t/4 + 8, two adjacent
+      // columns per 8-column block: every store instruction writes 8 rows x 32 B (whole sectors)
+      uint32_t r[16];
+      tmem_ld_16x256b_x4(tmem + 384 + (j & 1) * 64 + lane_off + wg * 32, r);
       tmem_wait_ld();
-      if (lane < 16 && q < S) {
-        float* dst = dq_base + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + wg * 32;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (DQ_ATOMIC) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
-                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
-                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
-                         : "memory");
-          } else {
-            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]),
-                                                                  __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+      for (int hh = 0; hh < 2; ++hh) {
+        const int q = j * BQ + quad * 16 + (lane >> 2) + hh * 8;
+        if (q < S) {
+          float* dst = dq_base + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + wg * 32 + (lane & 3) * 2;
+#pragma unroll
+          for (int jb = 0; jb < 4; ++jb) {
+            const float v0 = __uint_as_float(r[jb * 4 + hh * 2]), v1 = __uint_as_float(r[jb * 4 + hh * 2 + 1]);
+            if (DQ_ATOMIC) {
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + jb * 8), "f"(v0), "f"(v1) : "memory");
+            } else {
+              *reinterpret_cast<float2*>(dst + jb * 8) = make_float2(v0, v1);
+            }
           }
         }
       }
-    }
-    pc.lap(4);
-    tc_fence_before();
-    __syncthreads();  // dQ TMEM (= S^T columns) / P^T, dS^T smem are reused by the next chunk
-    pc.lap(5);
-    if (warp0) if (leader && i + 1 < n_q) { tc_fence_after(); issue_st(i + 1); }
-  }
-  pc.acc[6] = n_q;
-  // ---- dK, dV for this key tile (exclusive rows) ----
-  tc_fence_after();
+      pc.lap(4);
+    };
+
+    for (int i = 0; i < n_q; ++i) {
+      const int bb = i & 1;
+      const int q0 = i * BQ;
+      const int nu = nu_of(i);
+      mbar_wait(&bar_st[bb], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&bar_s[bb], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      pc.lap(0);
+      if (!warp_dead) {
+        const float* nlse = s_nlse + bb * BQ;
+        const float* dsm = s_dsum + bb * BQ;
+        uint8_t* pT = sPT + bb * 16384;
+        uint8_t* dT = sdST + bb * 16384;
+        // the TMEM loads of the second unit run under the arithmetic of the first (TMEM -> register bandwidth is ~64 B/clk per SM:
+        // S^T and dP^T of one chunk are 64 KB)
+        uint32_t rs[16], rd[16], rs2[16], rd2[16];
+        const int u0 = wg * 2;
+        if (u0 < nu) {
+          tmem_ld_32x16(tmem + bb * 64 + lane_off + u0 * 16, rs);
+          tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + u0 * 16, rd);
+          tmem_wait_ld_regs16x2(rs, rd);
+        }
+        if (u0 + 1 < nu) {
+          tmem_ld_32x16(tmem + bb * 64 + lane_off + (u0 + 1) * 16, rs2);
+          tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + (u0 + 1) * 16, rd2);
+        }
 #pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const uint32_t t = which == 0 ? tdK : tdV;
-    {
-      const int c = wg;
-      uint32_t r[32];
-      tmem_ld_32x32(t + lane_off + c * 32, r);
-      tmem_wait_ld();
-      if (k_in) {
-        bf16* dst = p.dqkv + (size_t)(tok0 + kk) * p.ld_dqkv + (which == 0 ? H : 2 * H) + h * AT_D + c * 32;
+        for (int uu = 0; uu < 2; ++uu) {
+          const int u = u0 + uu;
+          if (u >= nu) break;  // warp-uniform
+          if (uu == 1) {
+            tmem_wait_ld_regs16x2(rs2, rd2);  // the registers are threaded through the wait: no use can be scheduled above it
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk = make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])),
-                                pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
-                                pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
-                                pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
-          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+            for (int e = 0; e < 16; ++e) { rs[e] = rs2[e]; rd[e] = rd2[e]; }
+          }
+          const int qb = q0 + u * 16;
+          const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
+          const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
+          const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
+          uint32_t pk[8], dk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(nlse + u * 16 + e);
+            const float4 d4 = *reinterpret_cast<const float4*>(dsm + u * 16 + e);
+            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+            float pv[4], dv[4];
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+              float pr;
+              if (fast) {
+                pr = ex2_approx(fmaf(__uint_as_float(rs[e + t4]), sc2, ls[t4]));
+              } else {
+                float t = __uint_as_float(rs[e + t4]) * sc2;
+                t = vk ? t : MASKED_LOG2;
+                t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
+                pr = ex2_approx(t + ls[t4]);
+                pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
+              }
+              pv[t4] = pr;
+              // d(score)/d(q k^T) = m * scale (utils/transformer.py:109-110: scores*m - 1e10*(1-m)): a padding QUERY row keeps
+              // its uniform probabilities for dV but sends nothing back into q and k.  (scale itself: dK epilogue / dQ finish)
+              float g = pr;
+              if (!fast) g = ((qw >> (e + t4)) & 1u) ? g : 0.f;
+              dv[t4] = (__uint_as_float(rd[e + t4]) - ds[t4]) * g;
+            }
+            pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+            dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t off = sw128_offset(row_t, (uint32_t)(u * 2 + g));
+            *reinterpret_cast<uint4*>(pT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            *reinterpret_cast<uint4*>(dT + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+          }
         }
       }
+      pc.lap(1);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[bb]);
+      pc.lap(2);
+      if (i >= 1) drain(i - 1);
     }
+    drain(n_q - 1);  // also: every MMA of this CTA has completed (its commit covers all earlier ones)
+    pc.acc[6] = n_q;
+    // ---- dK (x 1/sqrt(d)), dV for this key tile (exclusive rows), transposed through the slot: 8 rows x 64 B per instruction ----
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint32_t r[32];
+      tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_off + wg * 32, r);
+      tmem_wait_ld();
+      const float mul = which == 0 ? p.scale : 1.0f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)  // the slot as [32 rows][64 B]: row `lane` = this thread's 32 bf16 values
+        *reinterpret_cast<uint4*>(slot + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * mul, __uint_as_float(r[g * 8 + 1]) * mul),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * mul, __uint_as_float(r[g * 8 + 3]) * mul),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * mul, __uint_as_float(r[g * 8 + 5]) * mul),
+                       pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * mul, __uint_as_float(r[g * 8 + 7]) * mul));
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(slot + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+        const int key = k0 + quad * 32 + rr;
+        if (key < S)
+          *reinterpret_cast<uint4*>(p.dqkv + (size_t)(tok0 + key) * p.ld_dqkv + (which == 0 ? H : 2 * H) + h * AT_D + wg * 32 + cc * 8) = v;
+      }
+      __syncwarp();
+    }
+    pc.lap(7);
+    pc.flush(p.dbg ? p.dbg + 8 : nullptr);
   }
-  pc.lap(7);
-  pc.flush(p.dbg ? p.dbg + 8 : nullptr);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // D[b,h,q] = sum_d dO[q,hd] * O[q,hd]   (one warp per (token, head) pair would waste lanes; 8 lanes x 8 elems per head)
@@ -600,7 +696,7 @@ __global__ void attn_dsum_kernel(const bf16* __restrict__ o, const bf16* __restr
 // atomically accumulated slice that is re-zeroed for the next layer.
 __global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict__ dq, int ld_dq, bf16* __restrict__ dqkv, int ld_dqkv,
                                                                long long rows, int H, float* __restrict__ bias_grad, int n_parts,
-                                                               size_t part_stride) {
+                                                               size_t part_stride, float scale) {
   __shared__ float sred[8][256];
   pdl_launch_dependents();
   pdl_wait();
@@ -625,7 +721,9 @@ __global__ void __launch_bounds__(256) attn_dqkv_finish_kernel(float* __restrict
             b.x += d.x; b.y += d.y; b.z += d.z; b.w += d.w;
           }
         }
-        const uint4 pk = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        // K3 accumulates dS' K without the 1/sqrt(d) of the scores: applied here, once per output element
+        const uint4 pk = make_uint4(pack_bf16x2(a.x * scale, a.y * scale), pack_bf16x2(a.z * scale, a.w * scale),
+                                    pack_bf16x2(b.x * scale, b.y * scale), pack_bf16x2(b.z * scale, b.w * scale));
         *reinterpret_cast<uint4*>(o) = pk;
         const uint32_t* pu = reinterpret_cast<const uint32_t*>(&pk);
 #pragma unroll
@@ -782,6 +880,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
 }
 
 static unsigned long long* g_attn_dbg = nullptr;  // merlot_attention_debug_counters
+static int g_attn_dbg_mode = 0;                   // merlot_attention_debug_mode
 
 static int check_common(const merlot_attn_t* a) {
   MB_REQUIRE(a != nullptr, MERLOT_EINVAL, "attention: null descriptor");
@@ -808,6 +907,7 @@ static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
   p->colsum_split = a->colsum_split;
   p->colsum_valid_q = a->colsum_valid_q;
   p->dbg = g_attn_dbg;
+  p->dbg_mode = g_attn_dbg_mode;
 }
 
 }  // namespace mb
@@ -815,6 +915,8 @@ static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
 using namespace mb;
 
 extern "C" void merlot_attention_debug_counters(void* buf_u64x16) { g_attn_dbg = reinterpret_cast<unsigned long long*>(buf_u64x16); }
+
+extern "C" void merlot_attention_debug_mode(int mode) { g_attn_dbg_mode = mode; }
 
 extern "C" int merlot_attention_fwd(const merlot_attn_t* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -889,18 +991,18 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
   }
   dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
   if (parts > 0) {
-    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, false>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
-    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, false>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));
+    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));
   } else {
-    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
-    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, grid, dim3(256), BWD_SMEM, stream, tkv, tq, tdo, p));
+    if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));
+    else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));
   }
   MB_CHECK_LAUNCH();
   {
     long long slabs = ceil_div_ll(tokens, 64);
     if (slabs > 128) slabs = 128;
     MB_CHECK_CUDA(launch_pdl(attn_dqkv_finish_kernel, dim3(ceil_div(3 * H, 256), (unsigned)slabs), dim3(256), 0, stream, a->dq_accum,
-                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv, parts, p.dq_part_stride));
+                             a->ld_dq, p.dqkv, a->ld_dqkv, tokens, H, a->d_bias_qkv, parts, p.dq_part_stride, a->scale));
     MB_CHECK_LAUNCH();
   }
   return MERLOT_OK;

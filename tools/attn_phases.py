@@ -27,7 +27,7 @@ for B, S, heads, masked in ((32, 266, 12, False), (8, 396, 12, True), (2, 3608, 
     dsum = torch.empty(B, heads, S, dtype=torch.float32, device=dev)
     ops.attention_bwd(qkv, ctx, dctx, lse, B, S, heads, valid, dqkv=dqkv, dq_accum=ws, dsum=dsum)
     torch.cuda.synchronize()
-    cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(24, dtype=torch.int64, device=dev)
     L.merlot_attention_debug_counters(C.c_void_p(cnt.data_ptr()))
     ops.attention_fwd(qkv, B, S, heads, valid, ctx=ctx, lse=lse)
     ops.attention_bwd(qkv, ctx, dctx, lse, B, S, heads, valid, dqkv=dqkv, dq_accum=ws, dsum=dsum)
@@ -42,3 +42,5 @@ for B, S, heads, masked in ((32, 266, 12, False), (8, 396, 12, True), (2, 3608, 
           f"   | per CTA: final wait {c[5] / nf:7.0f}  epilogue {c[7] / nf:7.0f}  tiles/CTA {tf / nf:.1f}")
     print("  K3 per q chunk  : " + "  ".join(f"{n} {c[8 + i] / tb:7.0f}" for i, n in enumerate(("wait1", "math", "fence+sync", "wait2", "dQ out", "sync2"))) +
           f"   | per CTA: epilogue {c[15] / nb:7.0f}  chunks/CTA {tb / nb:.1f}")
+    ti = max(c[22], 1)
+    print("  K3 issuer/chunk : " + "  ".join(f"{n} {c[16 + i] / ti:7.0f}" for i, n in enumerate(("wait P", "MMA2 issue", "stats", "MMA1 (+wait Q)", "refill"))))
