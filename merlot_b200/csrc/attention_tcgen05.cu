@@ -302,27 +302,33 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// backward (v3): warp-specialised, software-pipelined.  One CTA per (128-key tile, head, batch), 288 threads:
+// backward (v4): PERSISTENT, warp-specialised, software-pipelined.  One CTA per SM (320 threads) walks the work items
+// (128-key tile, head, batch) assigned to it round-robin; the pipeline never drains between items:
 //   warps 0-7  softmax / gradient arithmetic (two warps per TMEM lane quadrant; keys sit on the lanes),
-//   warp  8    issuer: TMA loads, every tcgen05.mma (one elected lane), per-chunk statistics staging (all 32 lanes).
-// The queries are walked in chunks of 64.  Per chunk i:
-//   MMA1(i):  S^T = K Q^T, dP^T = V dO^T                      -> TMEM buffers i & 1 (double-buffered: issued two chunks ahead)
-//   math(i):  P^T = exp2(S^T sc - lse), dS'^T = P^T (dP^T - D) -> bf16, 128B-swizzled smem buffers i & 1
-//   MMA2(i):  dV += P^T dO, dK += dS'^T Q (TMEM, whole key tile), dQ_chunk = dS' K (M = 64 accumulator, TMEM buffers i & 1)
-//   drain(i): dQ_chunk TMEM -> warp-private smem transposition -> coalesced fp32 stores
-// so the tensor pipe always has MMA2(i-1) / MMA1(i+1) queued while the arithmetic of chunk i runs; nothing in the loop is a
-// CTA-wide barrier (mbarriers between the issuer and the 8 arithmetic warps only).  1/sqrt(d) is applied once per output
-// (dK in the epilogue, dQ in attn_dqkv_finish) instead of once per score.
-// dQ never touches an atomic when the sequence has <= 4 key tiles: every CTA stores its partial for its key tile into its own
+//   warp  8    MMA issuer: every tcgen05.mma and commit (one elected lane) -- nothing else sits in its dependency chain,
+//   warp  9    loader: TMA loads (K/V per item, Q/dO chunk ring) and the per-chunk statistics ring (all 32 lanes).
+// The queries of an item are walked in chunks of 64; chunks are numbered globally (g) across the CTA's items.  Per chunk g:
+//   MMA1(g):  S^T = K Q^T, dP^T = V dO^T                      -> TMEM buffers g & 1 (issued two chunks ahead, across items)
+//   math(g):  P^T = exp2(S^T sc - lse), dS'^T = P^T (dP^T - D) -> bf16, 128B-swizzled smem buffers g & 1
+//   MMA2(g):  dV += P^T dO, dK += dS'^T Q (TMEM, whole key tile), dQ_chunk = dS' K (M = 64 accumulator, TMEM buffers g & 1)
+//   drain(g): dQ_chunk TMEM (16 live lanes) -> fp32 stores of whole sectors
+// K/V tiles are double-buffered per item, the Q/dO chunks run through a 4-stage ring; the only CTA-wide synchronisation is at
+// kernel start / end (mbarriers between the issuer and the 8 arithmetic warps, one named barrier when the batch element --
+// and with it the query-validity bitmask -- changes).  At an item's end the arithmetic warps read dK / dV out of TMEM while the
+// tensor pipe already runs the next item's S^T / dP^T.  (Measured on the non-persistent predecessor: 55 us of a 90 us launch
+// were per-CTA prologue / epilogue / pipeline fill -- profiles/r02_attn_bwd_v3_mode_experiments.txt.)
+// 1/sqrt(d) is applied once per output (dK in the epilogue, dQ in attn_dqkv_finish) instead of once per score.
+// dQ never touches an atomic when the sequence has <= 4 key tiles: every item stores its partial for its key tile into its own
 // slice of the [parts][tokens][H] fp32 workspace and attn_dqkv_finish sums the slices (bitwise reproducible); longer
 // sequences red.add into one slice.  Warps whose 32 keys all lie past the sequence end (ragged last key tile: S = 266 has 10
-// keys there) zero their P^T / dS^T rows once and skip the arithmetic.
+// keys there) zero their P^T / dS^T rows once per item and skip the arithmetic.
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int BQ = 64;              // queries per chunk
 constexpr int MAX_DQ_PARTS = 4;     // key tiles per sequence for which dQ goes through per-tile slices instead of atomics
-constexpr int BWD_QSTAGES = 4;      // Q/dO chunk ring
-constexpr int BWD_THREADS = 288;
-constexpr int BWD_SMEM = 16384 * 2 + BWD_QSTAGES * 16384 + 2 * 16384 + 2 * 16384 + 8 * 2048 + 1024 + 512 + 256 + 1024;
+constexpr int BWD_QSTAGES = 5;      // Q/dO chunk ring: the loader runs up to 5 chunks ahead of MMA2, 3 ahead of MMA1 (load latency ~1 us)
+constexpr int BWD_THREADS = 320;
+constexpr int BWD_STSTAGES = 4;     // statistics ring (chunks)
+constexpr int BWD_SMEM = 2 * 32768 + BWD_QSTAGES * 16384 + 2 * 16384 + 2 * 16384 + 2048 + 512 + 512 + 1024;
 
 template <bool HAS_MASK, bool DQ_ATOMIC>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -330,59 +336,45 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_do, const AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + 16384;
-  uint8_t* sQd = smem + 32768;                               // BWD_QSTAGES x { Q chunk 8 KB, dO chunk 8 KB }
+  uint8_t* sKV = smem;                                       // [2] x { K tile 16 KB, V tile 16 KB }
+  uint8_t* sQd = smem + 2 * 32768;                           // BWD_QSTAGES x { Q chunk 8 KB, dO chunk 8 KB }
   uint8_t* sPT = sQd + BWD_QSTAGES * 16384;                  // [2] P^T  [128 keys][64 q] bf16: one 128B-swizzled atom each
   uint8_t* sdST = sPT + 2 * 16384;                           // [2] dS^T same layout
-  uint8_t* sStg = sdST + 2 * 16384;                          // 8 warp-private 2 KB transposition slots
-  float* s_nlse = reinterpret_cast<float*>(sStg + 8 * 2048);  // [2][64]  -lse * log2(e)
-  float* s_dsum = s_nlse + 128;                              // [2][64]
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + 128);  // [MAX_MASK_WORDS] query validity bits
+  // (the 8 warp-private 2 KB transposition slots of the dK/dV epilogue live in the P^T buffer that the NEXT item's first chunk
+  //  does not use: every MMA of the item has completed by then, and no warp can reach the chunk after that one -- it needs all
+  //  eight warps' arrivals for the first -- before every warp has left its epilogue)
+  float* s_nlse = reinterpret_cast<float*>(sdST + 2 * 16384);  // [BWD_STSTAGES][64]  -lse * log2(e)
+  float* s_dsum = s_nlse + BWD_STSTAGES * BQ;                  // [BWD_STSTAGES][64]
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_dsum + BWD_STSTAGES * BQ);  // [MAX_MASK_WORDS] query validity bits of the current batch element
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_mask) + 512);
-  uint64_t *bar_kv = bars, *bar_q = bars + 1 /* [4] */, *bar_s = bars + 5 /* [2] */, *bar_st = bars + 7 /* [2] */, *bar_p = bars + 9 /* [2] */,
-           *bar_d = bars + 11 /* [2] */;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t *bar_kv = bars /* [2] full */, *bar_kvfree = bars + 2 /* [2] */, *bar_q = bars + 4 /* [<= 6] full */, *bar_qfree = bars + 10 /* [<= 6] */,
+           *bar_st = bars + 16 /* [4] full */, *bar_stfree = bars + 20 /* [4] */, *bar_s = bars + 24 /* [2] */, *bar_p = bars + 26 /* [2] */,
+           *bar_d = bars + 28 /* [2] */, *bar_acc = bars + 30;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 31);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (see attn_fwd_kernel)
   const bool leader = elect_one();
   const int wg = (warp >> 2) & 1, quad = warp & 3, row_t = quad * 32 + lane;
   pdl_launch_dependents();
-  const int k0 = blockIdx.x * AT_N, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S, H = p.H;
-  const int tok0 = b * S;
-  const int n_q = (S + BQ - 1) / BQ;
+  const int n_q = (S + BQ - 1) / BQ;           // chunks per item
+  const int n_kv = (S + AT_N - 1) / AT_N;      // key tiles per (head, batch)
+  const int total_items = n_kv * p.heads * p.B;
+  const int n_local = ((int)blockIdx.x < total_items) ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = n_local * n_q;                 // chunks this CTA walks
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_kv); tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do);
-    mbar_init(bar_kv, 1);
-    for (int i = 0; i < BWD_QSTAGES; ++i) mbar_init(&bar_q[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_st[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_d[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_kv[i], 1); mbar_init(&bar_kvfree[i], 1); }
+    for (int i = 0; i < BWD_QSTAGES; ++i) { mbar_init(&bar_q[i], 1); mbar_init(&bar_qfree[i], 1); }
+    for (int i = 0; i < BWD_STSTAGES; ++i) { mbar_init(&bar_st[i], 1); mbar_init(&bar_stfree[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 8); mbar_init(&bar_d[i], 1); }
+    mbar_init(bar_acc, 8);
     fence_barrier_init();
   }
   if (warp == 8) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
-  // a warp whose 32 keys are all out of range contributes exact zeros: written once (both buffers), arithmetic skipped afterwards
-  const bool warp_dead = warp < 8 && ((k0 + quad * 32) >= S || (p.dbg_mode & 1));
-  if (warp_dead && wg == 0) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        *reinterpret_cast<uint4*>(sPT + bb * 16384 + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(sdST + bb * 16384 + sw128_offset(row_t, c)) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-  }
   pdl_wait();
-  if (HAS_MASK && warp < 8) {
-    for (int k = tid; k < n_q * BQ; k += 256) {
-      const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
-      const uint32_t w = __ballot_sync(0xffffffffu, v);
-      if (lane == 0) s_mask[k >> 5] = w;
-    }
-  }
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -390,264 +382,331 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
   // TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256, dK 320, dQ[2] 384/448
   const uint32_t tdV = tmem + 256, tdK = tmem + 320;
   // a ragged last chunk only costs its 16-query units (S^T / dP^T with N = 16 nu, nu arithmetic units, nu k16-steps of dV / dK)
-  auto nu_of = [&](int i) { return min(BQ / 16, (S - i * BQ + 15) >> 4); };
+  auto nu_of = [&](int c) { return min(BQ / 16, (S - c * BQ + 15) >> 4); };
+  // item `it` of this CTA -> (key tile, head, batch)
+  auto decode = [&](int it, int& kt, int& hh, int& bb_) {
+    const int item = (int)blockIdx.x + it * (int)gridDim.x;
+    kt = item % n_kv;
+    const int rest = item / n_kv;
+    hh = rest % p.heads;
+    bb_ = rest / p.heads;
+  };
 
-  if (warp == 8) {
-    // ================================= issuer warp =================================
+  // Chunk cursors: (item, chunk-in-item), ring stages and their parities advanced incrementally -- an integer division per chunk
+  // in a single warp's issue path costs more than the MMAs it feeds (measured); the item decode runs once per item.
+  struct Cur {
+    int g, it, c, kt, h, b;
+    int st;        // Q/dO ring stage of chunk g
+    uint32_t sph;  // parity of that stage's current use
+  };
+  auto cur_init = [&](Cur& cu) { cu.g = 0; cu.it = 0; cu.c = 0; cu.st = 0; cu.sph = 0; decode(0, cu.kt, cu.h, cu.b); };
+  auto cur_next = [&](Cur& cu) {
+    ++cu.g;
+    if (++cu.st == BWD_QSTAGES) { cu.st = 0; cu.sph ^= 1u; }
+    if (++cu.c == n_q) { cu.c = 0; ++cu.it; if (cu.it < n_local) decode(cu.it, cu.kt, cu.h, cu.b); }
+  };
+
+  if (warp == 9) {
+    // ================================= loader warp =================================
+    // K/V tiles per item (2 buffers), Q/dO chunks (ring), statistics (-lse*log2e and D, ring of 4 chunks; the global loads are
+    // issued two chunks before the values are parked in smem).  Classic producer: waits on the "free" barrier of a slot with
+    // the inverted parity, so the first pass through a ring never blocks.
+    Cur cl, cf;
+    cur_init(cl); cur_init(cf);
+    float st_nl[2][2], st_ds[2][2];
+    auto fetch_stats = [&](const Cur& cu) {
+      const size_t o0 = ((size_t)cu.b * p.heads + cu.h) * S;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int q = cu.c * BQ + lane + r * 32;
+        const float nl = (q < S) ? p.lse[o0 + q] : 0.f, dd = (q < S) ? p.dsum[o0 + q] : 0.f;
+        if (cu.g & 1) { st_nl[1][r] = nl; st_ds[1][r] = dd; } else { st_nl[0][r] = nl; st_ds[0][r] = dd; }
+      }
+    };
+    for (int i = 0; i < 2 && i < G; ++i) { fetch_stats(cf); cur_next(cf); }
+    for (int L = 0; L < G; ++L) {
+      if (cl.c == 0) {  // first chunk of item cl.it: its K/V tiles
+        const int it = cl.it;
+        mbar_wait(&bar_kvfree[it & 1], (uint32_t)(((it >> 1) & 1) ^ 1));
+        if (leader) {
+          uint8_t* buf = sKV + (it & 1) * 32768;
+          mbar_arrive_expect_tx(&bar_kv[it & 1], 32768);
+          tma_load_2d(buf, &tm_kv, &bar_kv[it & 1], H + cl.h * AT_D, cl.b * S + cl.kt * AT_N);
+          tma_load_2d(buf + 16384, &tm_kv, &bar_kv[it & 1], 2 * H + cl.h * AT_D, cl.b * S + cl.kt * AT_N);
+        }
+      }
+      mbar_wait(&bar_qfree[cl.st], cl.sph ^ 1u);
+      if (leader) {
+        uint8_t* buf = sQd + cl.st * 16384;
+        mbar_arrive_expect_tx(&bar_q[cl.st], 16384);
+        tma_load_2d(buf, &tm_q, &bar_q[cl.st], cl.h * AT_D, cl.b * S + cl.c * BQ);
+        tma_load_2d(buf + 8192, &tm_do, &bar_q[cl.st], cl.h * AT_D, cl.b * S + cl.c * BQ);
+      }
+      {  // statistics of chunk L (fetched two iterations ago) -> ring slot L & 3
+        const int sb = L & (BWD_STSTAGES - 1);
+        mbar_wait(&bar_stfree[sb], (uint32_t)(((L / BWD_STSTAGES) & 1) ^ 1));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          s_nlse[sb * BQ + lane + r * 32] = -((L & 1) ? st_nl[1][r] : st_nl[0][r]) * LOG2E;
+          s_dsum[sb * BQ + lane + r * 32] = (L & 1) ? st_ds[1][r] : st_ds[0][r];
+        }
+        __syncwarp();
+        if (leader) mbar_arrive(&bar_st[sb]);
+        if (L + 2 < G) { fetch_stats(cf); cur_next(cf); }
+      }
+      cur_next(cl);
+    }
+  } else if (warp == 8) {
+    // ================================= MMA issuer warp =================================
     constexpr uint32_t idesc_dv = make_idesc_bf16(AT_N, AT_D, 0, 1);   // A = P^T/dS^T K-major (q), B = dO/Q MN-major
     constexpr uint32_t idesc_dq = make_idesc_bf16(BQ, AT_D, 1, 1);     // M = 64: A = dS (MN-major view of dS^T), B = K MN-major
-    const uint32_t ka = smem_u32(sK), va = smem_u32(sV);
-    auto load_q = [&](int i) {
-      if (leader) {
-        uint8_t* buf = sQd + (i & (BWD_QSTAGES - 1)) * 16384;
-        uint64_t* bq = &bar_q[i & (BWD_QSTAGES - 1)];
-        mbar_arrive_expect_tx(bq, 16384);
-        tma_load_2d(buf, &tm_q, bq, h * AT_D, tok0 + i * BQ);
-        tma_load_2d(buf + 8192, &tm_do, bq, h * AT_D, tok0 + i * BQ);
-      }
-    };
-    // -lse*log2e and D of query chunk i -> smem buffer i & 1 (all 32 lanes, 2 queries each).  The global loads are issued one
-    // loop iteration before the values are parked in smem, so their latency never sits in the issue path.
-    float st_nl[2], st_ds[2];
-    auto fetch_stats = [&](int i) {
-      const size_t o0 = ((size_t)b * p.heads + h) * S;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int q = i * BQ + lane + r * 32;
-        st_nl[r] = (q < S) ? -p.lse[o0 + q] * LOG2E : 0.f;
-        st_ds[r] = (q < S) ? p.dsum[o0 + q] : 0.f;
-      }
-    };
-    auto put_stats = [&](int i) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        s_nlse[(i & 1) * BQ + lane + r * 32] = st_nl[r];
-        s_dsum[(i & 1) * BQ + lane + r * 32] = st_ds[r];
-      }
-      __syncwarp();
-      if (leader) mbar_arrive(&bar_st[i & 1]);
-    };
-    auto issue_st = [&](int i) {  // MMA1: S^T and dP^T of query chunk i -> TMEM buffers i & 1
-      mbar_wait(&bar_q[i & (BWD_QSTAGES - 1)], (uint32_t)((i / BWD_QSTAGES) & 1));
+    int kv_ready = -1;  // last item whose K/V tiles this warp has seen land
+    auto issue_st = [&](const Cur& cu) {  // MMA1: S^T and dP^T of a chunk -> TMEM buffers g & 1
+      const int g = cu.g, it = cu.it;
+      if (it > kv_ready) { mbar_wait(&bar_kv[it & 1], (uint32_t)((it >> 1) & 1)); kv_ready = it; }
+      mbar_wait(&bar_q[cu.st], cu.sph);
       tc_fence_after();
       if (leader) {
-        const uint32_t qa = smem_u32(sQd + (i & (BWD_QSTAGES - 1)) * 16384), da = qa + 8192;
-        const uint32_t idesc_st = make_idesc_bf16(AT_N, nu_of(i) * 16, 0, 0);  // both operands K-major (d)
-        const uint32_t tST = tmem + (i & 1) * 64, tdPT = tmem + 128 + (i & 1) * 64;
+        const uint32_t ka = smem_u32(sKV + (it & 1) * 32768), va = ka + 16384;
+        const uint32_t qa = smem_u32(sQd + cu.st * 16384), da = qa + 8192;
+        const uint32_t idesc_st = make_idesc_bf16(AT_N, nu_of(cu.c) * 16, 0, 0);  // both operands K-major (d)
+        const uint32_t tST = tmem + (g & 1) * 64, tdPT = tmem + 128 + (g & 1) * 64;
         if (!(p.dbg_mode & 4)) {
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tST, desc_kmajor(ka, k), desc_kmajor(qa, k), idesc_st, k > 0);
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) umma_bf16_ss(tdPT, desc_kmajor(va, k), desc_kmajor(da, k), idesc_st, k > 0);
         }
-        umma_commit(&bar_s[i & 1]);
+        umma_commit(&bar_s[g & 1]);
       }
     };
-    if (leader) {
-      mbar_arrive_expect_tx(bar_kv, 32768);
-      tma_load_2d(sK, &tm_kv, bar_kv, H + h * AT_D, tok0 + k0);
-      tma_load_2d(sV, &tm_kv, bar_kv, 2 * H + h * AT_D, tok0 + k0);
-    }
-    for (int i = 0; i < BWD_QSTAGES && i < n_q; ++i) load_q(i);
-    fetch_stats(0); put_stats(0);
-    if (n_q > 1) { fetch_stats(1); put_stats(1); }
-    if (n_q > 2) fetch_stats(2);
-    mbar_wait(bar_kv, 0);
-    issue_st(0);
-    if (n_q > 1) issue_st(1);
+    Cur c_m1, c_m2;  // next chunk to run MMA1 / MMA2 on
+    cur_init(c_m1); cur_init(c_m2);
+    if (G > 0) { issue_st(c_m1); cur_next(c_m1); }
+    if (G > 1) { issue_st(c_m1); cur_next(c_m1); }
     PhaseClock ic(p.dbg != nullptr && leader);
-    for (int i = 0; i < n_q; ++i) {
-      const int bb = i & 1;
-      const int nu = nu_of(i);
-      mbar_wait(&bar_p[bb], (uint32_t)((i >> 1) & 1));  // P^T / dS^T of chunk i are in smem; its S^T / dP^T / statistics buffers
-      tc_fence_after();                                 // are free; dQ[bb] of chunk i-2 has been drained (program order per warp)
+    for (int g = 0; g < G; ++g) {
+      const int bb = g & 1;
+      const int it = c_m2.it, c = c_m2.c;
+      const int nu = nu_of(c);
+      if (c == 0 && it > 0) mbar_wait(bar_acc, (uint32_t)((it - 1) & 1));  // dK / dV of the previous item have left TMEM
+      mbar_wait(&bar_p[bb], (uint32_t)((g >> 1) & 1));  // P^T / dS^T of chunk g are in smem; its S^T / dP^T buffers are free;
+      tc_fence_after();                                 // dQ[bb] of chunk g-2 has been drained (program order per warp)
       ic.lap(0);
       if (leader) {
         const uint32_t pa = smem_u32(sPT + bb * 16384), sa = smem_u32(sdST + bb * 16384);
-        const uint32_t qa = smem_u32(sQd + (i & (BWD_QSTAGES - 1)) * 16384), da = qa + 8192;
+        const uint32_t qa = smem_u32(sQd + c_m2.st * 16384), da = qa + 8192;
+        const uint32_t ka = smem_u32(sKV + (it & 1) * 32768);
         const uint32_t tdQ = tmem + 384 + bb * 64;
         if (!(p.dbg_mode & 2)) {
 #pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (contraction over q)
-          if (k < nu) umma_bf16_ss(tdV, desc_kmajor(pa, k), desc_mnmajor(da, k, 0), idesc_dv, (i > 0 || k > 0));
+          for (int k = 0; k < BQ / 16; ++k)  // dV += P^T dO   (contraction over q)
+            if (k < nu) umma_bf16_ss(tdV, desc_kmajor(pa, k), desc_mnmajor(da, k, 0), idesc_dv, (c > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
-          if (k < nu) umma_bf16_ss(tdK, desc_kmajor(sa, k), desc_mnmajor(qa, k, 0), idesc_dv, (i > 0 || k > 0));
+          for (int k = 0; k < BQ / 16; ++k)  // dK += dS^T Q
+            if (k < nu) umma_bf16_ss(tdK, desc_kmajor(sa, k), desc_mnmajor(qa, k, 0), idesc_dv, (c > 0 || k > 0));
+          const int nk = min(AT_N / 16, (S - c_m2.kt * AT_N + 15) >> 4);  // a ragged last key tile contracts over its keys only
 #pragma unroll
-        for (int k = 0; k < AT_N / 16; ++k)  // dQ_chunk = dS K  (contraction over the 128 keys; stale columns of a ragged chunk
-          umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 0), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);  // only feed rows that are never stored)
+          for (int k = 0; k < AT_N / 16; ++k)  // dQ_chunk = dS K  (contraction over the keys; stale columns of a ragged chunk
+            if (k < nk) umma_bf16_ss(tdQ, desc_mnmajor(sa, k, 0), desc_mnmajor(ka, k, 0), idesc_dq, k > 0);  // only feed rows never stored)
         }
-        umma_commit(&bar_d[bb]);
+        umma_commit(&bar_d[bb]);               // dQ[bb] ready; P^T / dS^T[bb] free
+        umma_commit(&bar_qfree[c_m2.st]);      // this chunk's Q/dO ring stage is free
+        if (c == n_q - 1) umma_commit(&bar_kvfree[it & 1]);  // the item's K/V buffer is free
       }
       ic.lap(1);
-      if (i + 2 < n_q) {
-        put_stats(i + 2);  // fetched during the previous iteration
-        if (i + 3 < n_q) fetch_stats(i + 3);
-        ic.lap(2);
-        issue_st(i + 2);
-        ic.lap(3);
-      }
-      if (i >= 1 && i + 3 < n_q) {  // refill the ring: the stage of chunk i-1 is free once MMA2(i-1) has read it
-        mbar_wait(&bar_d[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-        load_q(i + 3);
-      }
-      ic.lap(4);
+      if (g + 2 < G) { issue_st(c_m1); cur_next(c_m1); }
+      ic.lap(3);
+      cur_next(c_m2);
     }
-    ic.acc[6] = n_q;
+    ic.acc[6] = G;
     ic.flush(p.dbg ? p.dbg + 16 : nullptr);
   } else {
     // ================================= arithmetic warps =================================
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const int kk = k0 + row_t;  // this thread's key row
-    const bool k_in = kk < S;
-    const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
     const float sc2 = p.scale * LOG2E;
-    float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)blockIdx.x * p.dq_part_stride);
-    uint8_t* slot = sStg + warp * 2048;  // [16 rows][128 B], 16-byte chunks XOR-swizzled by the row
     PhaseClock pc(p.dbg != nullptr && tid == 32);
-
-    // dQ partial of chunk j: M = 64 accumulator, row 16*quad + l lives on lane 32*quad + l (l < 16); this warp owns columns
-    // [32 wg, 32 wg + 32).  Transposed through the warp's slot so that every store instruction writes 4 full 128-byte lines.
-    auto drain = [&](int j) {
-      mbar_wait(&bar_d[j & 1], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      pc.lap(3);
-      // 16x256b: only the 16 live lanes of the M = 64 accumulator are read; thread t holds rows t/4 and t/4 + 8, two adjacent
-      // columns per 8-column block: every store instruction writes 8 rows x 32 B (whole sectors)
-      uint32_t r[16];
-      tmem_ld_16x256b_x4(tmem + 384 + (j & 1) * 64 + lane_off + wg * 32, r);
-      tmem_wait_ld();
+    int cur_b = -1;
+    for (int it = 0; it < n_local; ++it) {
+      int kt, h, b;
+      decode(it, kt, h, b);
+      const int k0 = kt * AT_N, tok0 = b * S;
+      if (HAS_MASK && b != cur_b) {  // query-validity bitmask of this batch element (every warp is past the previous item here)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int k = tid; k < n_q * BQ; k += 256) {
+          const bool v = (k < S) ? (p.valid[tok0 + k] != 0) : false;
+          const uint32_t w = __ballot_sync(0xffffffffu, v);
+          if (lane == 0) s_mask[k >> 5] = w;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      cur_b = b;
+      const int kk = k0 + row_t;  // this thread's key row
+      const bool k_in = kk < S;
+      const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
+      // a warp whose 32 keys are all out of range contributes exact zeros: written once per item (both buffers: every MMA of
+      // the previous item has completed -- its last drain waited for that), arithmetic skipped afterwards
+      const bool warp_dead = (k0 + quad * 32) >= S || (p.dbg_mode & 1);
+      if (warp_dead && wg == 0) {
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int q = j * BQ + quad * 16 + (lane >> 2) + hh * 8;
-        if (q < S) {
-          float* dst = dq_base + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + wg * 32 + (lane & 3) * 2;
+        for (int c8 = 0; c8 < 8; ++c8) {
 #pragma unroll
-          for (int jb = 0; jb < 4; ++jb) {
-            const float v0 = __uint_as_float(r[jb * 4 + hh * 2]), v1 = __uint_as_float(r[jb * 4 + hh * 2 + 1]);
-            if (DQ_ATOMIC) {
-              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + jb * 8), "f"(v0), "f"(v1) : "memory");
-            } else {
-              *reinterpret_cast<float2*>(dst + jb * 8) = make_float2(v0, v1);
-            }
+          for (int b2 = 0; b2 < 2; ++b2) {
+            *reinterpret_cast<uint4*>(sPT + b2 * 16384 + sw128_offset(row_t, c8)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sdST + b2 * 16384 + sw128_offset(row_t, c8)) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }
-      pc.lap(4);
-    };
+      float* dq_base = p.dq_accum + (DQ_ATOMIC ? (size_t)0 : (size_t)kt * p.dq_part_stride);
 
-    for (int i = 0; i < n_q; ++i) {
-      const int bb = i & 1;
-      const int q0 = i * BQ;
-      const int nu = nu_of(i);
-      mbar_wait(&bar_st[bb], (uint32_t)((i >> 1) & 1));
-      mbar_wait(&bar_s[bb], (uint32_t)((i >> 1) & 1));
-      tc_fence_after();
-      pc.lap(0);
-      if (!warp_dead) {
-        const float* nlse = s_nlse + bb * BQ;
-        const float* dsm = s_dsum + bb * BQ;
-        uint8_t* pT = sPT + bb * 16384;
-        uint8_t* dT = sdST + bb * 16384;
-        // the TMEM loads of the second unit run under the arithmetic of the first (TMEM -> register bandwidth is ~64 B/clk per SM:
-        // S^T and dP^T of one chunk are 64 KB)
-        uint32_t rs[16], rd[16], rs2[16], rd2[16];
-        const int u0 = wg * 2;
-        if (u0 < nu) {
-          tmem_ld_32x16(tmem + bb * 64 + lane_off + u0 * 16, rs);
-          tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + u0 * 16, rd);
-          tmem_wait_ld_regs16x2(rs, rd);
-        }
-        if (u0 + 1 < nu) {
-          tmem_ld_32x16(tmem + bb * 64 + lane_off + (u0 + 1) * 16, rs2);
-          tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + (u0 + 1) * 16, rd2);
-        }
+      // dQ partial of chunk c (global index g): M = 64 accumulator, row 16*quad + l on lane 32*quad + l (l < 16); this warp owns
+      // columns [32 wg, 32 wg + 32).  16x256b: only the 16 live lanes are read; thread t holds rows t/4 and t/4 + 8, two adjacent
+      // columns per 8-column block: every store instruction writes 8 rows x 32 B (whole sectors).
+      auto drain = [&](int c, int g) {
+        mbar_wait(&bar_d[g & 1], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        pc.lap(3);
+        uint32_t r[16];
+        tmem_ld_16x256b_x4(tmem + 384 + (g & 1) * 64 + lane_off + wg * 32, r);
+        tmem_wait_ld();
 #pragma unroll
-        for (int uu = 0; uu < 2; ++uu) {
-          const int u = u0 + uu;
-          if (u >= nu) break;  // warp-uniform
-          if (uu == 1) {
-            tmem_wait_ld_regs16x2(rs2, rd2);  // the registers are threaded through the wait: no use can be scheduled above it
+        for (int hh = 0; hh < 2; ++hh) {
+          const int q = c * BQ + quad * 16 + (lane >> 2) + hh * 8;
+          if (q < S) {
+            float* dst = dq_base + (size_t)(tok0 + q) * p.ld_dq + h * AT_D + wg * 32 + (lane & 3) * 2;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { rs[e] = rs2[e]; rd[e] = rd2[e]; }
-          }
-          const int qb = q0 + u * 16;
-          const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
-          const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
-          const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
-          uint32_t pk[8], dk[8];
-#pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(nlse + u * 16 + e);
-            const float4 d4 = *reinterpret_cast<const float4*>(dsm + u * 16 + e);
-            const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
-            float pv[4], dv[4];
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-              float pr;
-              if (fast) {
-                pr = ex2_approx(fmaf(__uint_as_float(rs[e + t4]), sc2, ls[t4]));
+            for (int jb = 0; jb < 4; ++jb) {
+              const float v0 = __uint_as_float(r[jb * 4 + hh * 2]), v1 = __uint_as_float(r[jb * 4 + hh * 2 + 1]);
+              if (DQ_ATOMIC) {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + jb * 8), "f"(v0), "f"(v1) : "memory");
               } else {
-                float t = __uint_as_float(rs[e + t4]) * sc2;
-                t = vk ? t : MASKED_LOG2;
-                t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
-                pr = ex2_approx(t + ls[t4]);
-                pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
+                *reinterpret_cast<float2*>(dst + jb * 8) = make_float2(v0, v1);
               }
-              pv[t4] = pr;
-              // d(score)/d(q k^T) = m * scale (utils/transformer.py:109-110: scores*m - 1e10*(1-m)): a padding QUERY row keeps
-              // its uniform probabilities for dV but sends nothing back into q and k.  (scale itself: dK epilogue / dQ finish)
-              float g = pr;
-              if (!fast) g = ((qw >> (e + t4)) & 1u) ? g : 0.f;
-              dv[t4] = (__uint_as_float(rd[e + t4]) - ds[t4]) * g;
             }
-            pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-            dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const uint32_t off = sw128_offset(row_t, (uint32_t)(u * 2 + g));
-            *reinterpret_cast<uint4*>(pT + off) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-            *reinterpret_cast<uint4*>(dT + off) = make_uint4(dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
           }
         }
+        pc.lap(4);
+      };
+
+      for (int c = 0; c < n_q; ++c) {
+        const int g = it * n_q + c;
+        const int bb = g & 1;
+        const int q0 = c * BQ;
+        const int nu = nu_of(c);
+        const int sb = g & (BWD_STSTAGES - 1);
+        mbar_wait(&bar_st[sb], (uint32_t)((g / BWD_STSTAGES) & 1));
+        mbar_wait(&bar_s[bb], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        pc.lap(0);
+        if (!warp_dead) {
+          const float* nlse = s_nlse + sb * BQ;
+          const float* dsm = s_dsum + sb * BQ;
+          uint8_t* pT = sPT + bb * 16384;
+          uint8_t* dT = sdST + bb * 16384;
+          // the TMEM loads of the second unit run under the arithmetic of the first (TMEM -> register bandwidth is ~64 B/clk per
+          // SM: S^T and dP^T of one chunk are 64 KB)
+          uint32_t rs[16], rd[16], rs2[16], rd2[16];
+          const int u0 = wg * 2;
+          if (u0 < nu) {
+            tmem_ld_32x16(tmem + bb * 64 + lane_off + u0 * 16, rs);
+            tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + u0 * 16, rd);
+            tmem_wait_ld_regs16x2(rs, rd);
+          }
+          if (u0 + 1 < nu) {
+            tmem_ld_32x16(tmem + bb * 64 + lane_off + (u0 + 1) * 16, rs2);
+            tmem_ld_32x16(tmem + 128 + bb * 64 + lane_off + (u0 + 1) * 16, rd2);
+          }
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            const int u = u0 + uu;
+            if (u >= nu) break;  // warp-uniform
+            if (uu == 1) {
+              tmem_wait_ld_regs16x2(rs2, rd2);  // the registers are threaded through the wait: no use can be scheduled above it
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { rs[e] = rs2[e]; rd[e] = rd2[e]; }
+            }
+            const int qb = q0 + u * 16;
+            const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
+            const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
+            const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
+            uint32_t pk[8], dk[8];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(nlse + u * 16 + e);
+              const float4 d4 = *reinterpret_cast<const float4*>(dsm + u * 16 + e);
+              const float ls[4] = {l4.x, l4.y, l4.z, l4.w}, ds[4] = {d4.x, d4.y, d4.z, d4.w};
+              float pv[4], dv[4];
+#pragma unroll
+              for (int t4 = 0; t4 < 4; ++t4) {
+                float pr;
+                if (fast) {
+                  pr = ex2_approx(fmaf(__uint_as_float(rs[e + t4]), sc2, ls[t4]));
+                } else {
+                  float t = __uint_as_float(rs[e + t4]) * sc2;
+                  t = vk ? t : MASKED_LOG2;
+                  t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
+                  pr = ex2_approx(t + ls[t4]);
+                  pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
+                }
+                pv[t4] = pr;
+                // d(score)/d(q k^T) = m * scale (utils/transformer.py:109-110: scores*m - 1e10*(1-m)): a padding QUERY row keeps
+                // its uniform probabilities for dV but sends nothing back into q and k.  (scale itself: dK epilogue / dQ finish)
+                float gq = pr;
+                if (!fast) gq = ((qw >> (e + t4)) & 1u) ? gq : 0.f;
+                dv[t4] = (__uint_as_float(rd[e + t4]) - ds[t4]) * gq;
+              }
+              pk[(e >> 1)] = pack_bf16x2(pv[0], pv[1]); pk[(e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+              dk[(e >> 1)] = pack_bf16x2(dv[0], dv[1]); dk[(e >> 1) + 1] = pack_bf16x2(dv[2], dv[3]);
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const uint32_t off = sw128_offset(row_t, (uint32_t)(u * 2 + g2));
+              *reinterpret_cast<uint4*>(pT + off) = make_uint4(pk[g2 * 4], pk[g2 * 4 + 1], pk[g2 * 4 + 2], pk[g2 * 4 + 3]);
+              *reinterpret_cast<uint4*>(dT + off) = make_uint4(dk[g2 * 4], dk[g2 * 4 + 1], dk[g2 * 4 + 2], dk[g2 * 4 + 3]);
+            }
+          }
+        }
+        pc.lap(1);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_p[bb]); mbar_arrive(&bar_stfree[sb]); }
+        pc.lap(2);
+        if (c >= 1) drain(c - 1, g - 1);
       }
-      pc.lap(1);
-      fence_proxy_async_smem();
+      drain(n_q - 1, it * n_q + n_q - 1);  // also: every MMA of this item has completed (its commit covers all earlier ones)
+      // ---- dK (x 1/sqrt(d)), dV for this key tile (exclusive rows), transposed through the slot: 8 rows x 64 B per instruction ----
+      uint8_t* slot = sPT + ((((it + 1) * n_q) & 1) ^ 1) * 16384 + warp * 2048;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        uint32_t r[32];
+        tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_off + wg * 32, r);
+        tmem_wait_ld();
+        const float mul = which == 0 ? p.scale : 1.0f;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4)  // the slot as [32 rows][64 B]: row `lane` = this thread's 32 bf16 values
+          *reinterpret_cast<uint4*>(slot + lane * 64 + ((g4 ^ ((lane >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16x2(__uint_as_float(r[g4 * 8 + 0]) * mul, __uint_as_float(r[g4 * 8 + 1]) * mul),
+                         pack_bf16x2(__uint_as_float(r[g4 * 8 + 2]) * mul, __uint_as_float(r[g4 * 8 + 3]) * mul),
+                         pack_bf16x2(__uint_as_float(r[g4 * 8 + 4]) * mul, __uint_as_float(r[g4 * 8 + 5]) * mul),
+                         pack_bf16x2(__uint_as_float(r[g4 * 8 + 6]) * mul, __uint_as_float(r[g4 * 8 + 7]) * mul));
+        __syncwarp();
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int rr = i4 * 8 + (lane >> 2), cc = lane & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(slot + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+          const int key = k0 + quad * 32 + rr;
+          if (key < S)
+            *reinterpret_cast<uint4*>(p.dqkv + (size_t)(tok0 + key) * p.ld_dqkv + (which == 0 ? H : 2 * H) + h * AT_D + wg * 32 + cc * 8) = v;
+        }
+        __syncwarp();
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[bb]);
-      pc.lap(2);
-      if (i >= 1) drain(i - 1);
+      if (lane == 0) mbar_arrive(bar_acc);  // dK / dV are out of TMEM: the next item's MMA2 may overwrite them
+      pc.lap(7);
     }
-    drain(n_q - 1);  // also: every MMA of this CTA has completed (its commit covers all earlier ones)
-    pc.acc[6] = n_q;
-    // ---- dK (x 1/sqrt(d)), dV for this key tile (exclusive rows), transposed through the slot: 8 rows x 64 B per instruction ----
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint32_t r[32];
-      tmem_ld_32x32((which == 0 ? tdK : tdV) + lane_off + wg * 32, r);
-      tmem_wait_ld();
-      const float mul = which == 0 ? p.scale : 1.0f;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)  // the slot as [32 rows][64 B]: row `lane` = this thread's 32 bf16 values
-        *reinterpret_cast<uint4*>(slot + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) =
-            make_uint4(pack_bf16x2(__uint_as_float(r[g * 8 + 0]) * mul, __uint_as_float(r[g * 8 + 1]) * mul),
-                       pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * mul, __uint_as_float(r[g * 8 + 3]) * mul),
-                       pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * mul, __uint_as_float(r[g * 8 + 5]) * mul),
-                       pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * mul, __uint_as_float(r[g * 8 + 7]) * mul));
-      __syncwarp();
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int rr = it * 8 + (lane >> 2), cc = lane & 3;
-        const uint4 v = *reinterpret_cast<const uint4*>(slot + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
-        const int key = k0 + quad * 32 + rr;
-        if (key < S)
-          *reinterpret_cast<uint4*>(p.dqkv + (size_t)(tok0 + key) * p.ld_dqkv + (which == 0 ? H : 2 * H) + h * AT_D + wg * 32 + cc * 8) = v;
-      }
-      __syncwarp();
-    }
-    pc.lap(7);
+    pc.acc[6] = G;
     pc.flush(p.dbg ? p.dbg + 8 : nullptr);
   }
   tc_fence_before();
@@ -989,7 +1048,8 @@ extern "C" int merlot_attention_bwd(const merlot_attn_t* a, void* stream_) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr = true;
   }
-  dim3 grid(ceil_div(a->S, AT_N), a->heads, a->B);
+  const long long items = (long long)ceil_div(a->S, AT_N) * a->heads * a->B;
+  dim3 grid((unsigned)(items < num_sms() ? items : num_sms()));  // persistent: one CTA per SM walks the (key tile, head, batch) items
   if (parts > 0) {
     if (a->valid) MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));
     else MB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, tkv, tq, tdo, p));

@@ -84,6 +84,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Whole-warp wait through ONE polling lane: 32 lanes spinning on mbarrier.try_wait serialise in the sync unit (measured in the
+// attention kernels: ~700-1000 cycles per wait against ~150 for a single lane); __syncwarp orders the other lanes behind it.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
