@@ -627,6 +627,48 @@ class MerlotOracle:
         return info["loss"] * cfg.get("temporal_coef", 1.0), info
 
 
+def contrastive_loss_replicas(models, rank: int):
+    """contrastive_loss of replica `rank` when `models` holds EVERY data-parallel replica (model/modeling.py:491-526 with
+    tpu_cross_replica_stack, utils/model_utils.py:673-707: every replica scatters its features into slot `replica_id` of a
+    zero tensor and cross_replica_sum fills in the others, so `all_*` = the replicas' features stacked in replica order and
+    the labels are shifted by rank * batch (:519)).  Built on one autograd graph, the gradient that flows into the OTHER
+    replicas' features is the cross_replica_sum's gradient (a sum over replicas = the reduce-scatter of the CUDA path)."""
+    me = models[rank]
+    cfg = me.config
+    inter = cfg.get("do_projection", False)
+    feats = []
+    for m in models:
+        if not hasattr(m, "_ctr_feats"):
+            m._ctr_feats = (m.project_and_norm(m.lang_trg_h, "lang_proj", inter), m.project_and_norm(m.img_trg_h, "viz_proj", inter))
+        feats.append(m._ctr_feats)
+    lx, vx = feats[rank]
+    all_l = torch.cat([f[0] for f in feats], 0)
+    all_v = torch.cat([f[1] for f in feats], 0)
+    temp = cfg.get("contrast_temp", 0.05)
+    n = lx.shape[0]
+    labels = torch.arange(n) + rank * n
+    losses = {}
+    for name, x, y in (("lang_to_viz", lx, all_v), ("viz_to_lang", vx, all_l)):
+        losses[name] = raw_cross_entropy_with_logits(x @ y.t() / temp, labels).mean()
+    losses["loss_all"] = cfg.get("contrast_coef", 1.0) * (losses["lang_to_viz"] + losses["viz_to_lang"]) / 2
+    return losses["loss_all"], losses
+
+
+def pretrain_losses_replicas(models, shuffled_idx_imgs, video_src_ids_list):
+    """Per-replica model_fn losses (model/modeling.py:700-713) of a data-parallel step, and their MEAN -- whose gradient is what
+    CrossShardOptimizer applies (utils/optimization.py:241-245: gradients averaged over replicas)."""
+    per = []
+    for r, m in enumerate(models):
+        lang_loss, _ = m.mask_loss()
+        contr_loss, _ = contrastive_loss_replicas(models, r)
+        if m.config.get("temporal_coef", 1.0) > 0.0:
+            temp_loss, _ = m.temporal_loss(shuffled_idx_imgs[r], video_src_ids_list[r])
+        else:
+            temp_loss = 0.0
+        per.append(lang_loss + contr_loss + temp_loss)
+    return sum(per) / len(per), per
+
+
 def pretrain_losses(model: MerlotOracle, shuffled_idx_img, video_src_ids):
     """model_fn loss sum, model/modeling.py:700-713."""
     lang_loss, lang = model.mask_loss()

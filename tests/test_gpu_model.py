@@ -184,3 +184,25 @@ def test_full_size_properties():
         s = fn(feats)
         s.train_op()
     assert fn(feats).loss < l0  # the step trains
+
+
+def test_partial_stack_backward_equals_full(tiny_cfg):
+    """merlot_stack_backward walked in layer groups (bwd_lo/bwd_hi; data-parallel bucket overlap) gives the gradients of one
+    full call (the only difference allowed is the order of fp32 atomic adds in split-K wgrads / LN column sums)."""
+    from merlot_b200.modeling import MerlotModel
+    cfg = dict(tiny_cfg, num_vision_transformer_hidden_layers=4)
+    image, ids, shuf, vid = synth(cfg, 2, 4, 16, 64, 96, 0)
+    params, store, _ = build(cfg)
+    draws = O.make_mask_draws(4, 32, 6, cfg["vocab_size"], seed=5)
+    gs = []
+    for groups in (None, [(2, 4), (1, 2), (0, 1)]):
+        m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                        shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=True)
+        m.mask_loss(), m.contrastive_loss(), m.temporal_loss(shuf.to(DEV), vid.to(DEV))
+        store.g.zero_()
+        seen = []
+        m.backward(vit_layer_groups=groups, on_vit_group_done=seen.append)
+        gs.append(store.g.clone())
+        assert seen == ([] if groups is None else [0, 1, 2])
+    assert rel(gs[1], gs[0]) < 1e-3
+    store.g.zero_()

@@ -211,3 +211,52 @@ def test_sort_story_scoring_matches_loop_restatement():
     assert ev["stories"] == [(0, 1, 2, 3, 4), (4, 3, 2, 1, 0)] and ev["pairwise"] == 0.5 and abs(ev["spearman"]) < 1e-12
     with pytest.raises(ValueError):
         S.permutation_scores(np.ones((5, 4, 3)))
+
+
+def test_vit_gradient_buckets_partition_the_vit_ranges():
+    """train.py's bucketed all-reduce: the buckets are disjoint, ordered top-down and cover exactly the ViT part of the arena."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from merlot_b200.params import ParamStore
+    cfg = bench.load_config()
+    st = ParamStore(cfg.model, device="cpu", optimizer_cfg=cfg.optimizer)
+    for n in (1, 3, 4, 12):
+        groups, ranges = st.vit_buckets(n)
+        assert groups[0][1] == 12 and groups[-1][0] == 0 and all(groups[i][0] == groups[i + 1][1] for i in range(len(groups) - 1))
+        flat = sorted(r for rs in ranges for r in rs)
+        assert all(flat[i][1] <= flat[i + 1][0] for i in range(len(flat) - 1))                      # disjoint
+        assert sum(b - a for a, b in flat) == sum(b - a for a, b in st.vit_ranges)                   # complete
+        for (lo, hi), rs in zip(groups[:-1], ranges[:-1]):                                           # a bucket holds exactly its layers' kernels
+            names = [e.name for e in st.entries.values() if any(a <= e.offset < b for a, b in rs)]
+            assert names and all(lo <= int(nm.split("/layer")[1][:2]) < hi and nm.endswith("/kernel") for nm in names)
+
+
+def test_multi_replica_contrastive_restatement_reduces_to_single_replica():
+    """oracle.contrastive_loss_replicas with one replica == MerlotOracle.contrastive_loss; with two, labels are shifted by
+    rank * N (model/modeling.py:519) and each replica sees the other's features as extra negatives."""
+    import torch
+    from oracle import merlot_oracle as O
+    from tests.test_gpu_model import synth
+    cfg = dict(use_bfloat16=True, hidden_size=64, vocab_size=500, patch_size=16, spatial_pool_size=2, num_attention_heads=1,
+               num_hidden_layers=1, num_vision_transformer_hidden_layers=1, num_lang_transformer_hidden_layers=1, intermediate_size=128,
+               initializer_range=0.02, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=64,
+               num_chunks_in_group=2, do_projection=True, do_bias=True, contrastive_size=64, contrast_coef=0.25, contrast_temp=0.05,
+               image_shuffle_prob=0.4, masking_rate=0.2, resnet_layers=[])
+    params = O.init_params(cfg, seed=1, perturb=0.05)
+    data = [synth(cfg, 2, 2, 16, 32, 48, 10 + r) for r in range(2)]
+    oms = [O.MerlotOracle(cfg, params, d[0], d[1], mask_input=True, shuffled_idx_img=d[2], mask_draws=O.make_mask_draws(2, 32, 6, 500, seed=3)) for d in data]
+    single, _ = oms[0].contrastive_loss()
+    one, _ = O.contrastive_loss_replicas([oms[0]], 0)
+    assert float(single) == float(one)
+    two0, _ = O.contrastive_loss_replicas(oms, 0)
+    two1, _ = O.contrastive_loss_replicas(oms, 1)
+    assert float(two0) > float(single)  # more negatives, same positives => larger cross entropy
+    # replica 1's positives sit at columns N..2N-1 of the gathered matrix
+    lx, vx = oms[1]._ctr_feats
+    all_v = torch.cat([oms[0]._ctr_feats[1], vx], 0)
+    logits = lx @ all_v.t() / 0.05
+    n = lx.shape[0]
+    assert torch.allclose(O.raw_cross_entropy_with_logits(logits, torch.arange(n) + n).mean() * 0.125 +
+                          O.raw_cross_entropy_with_logits(vx @ torch.cat([oms[0]._ctr_feats[0], lx], 0).t() / 0.05, torch.arange(n) + n).mean() * 0.125,
+                          two1)
