@@ -53,7 +53,10 @@ void merlot_reset_launch_count(void);
  * Epilogue, applied in this order per element (row m, column n):
  *   v = alpha*acc; v += bias[n]; if GELU: {pre=v; v=gelu_erf(v)}; if MUL_DGELU: v *= gelu_erf'(aux[m,n]);
  *   if DROPOUT: v = keep(m,n) ? v/(1-p) : 0; v += resid[m,n]; store.
- *   With GELU and out2 != NULL: out <- pre (bf16), out2 <- gelu(pre).
+ *   With GELU and out2 != NULL: out <- pre (bf16), out2 <- gelu(pre); with GELU_GRAD_OUT as well: out <- gelu_erf'(pre) instead
+ *   of pre -- the factor the FFN2 dgrad needs, computed where exp(-pre^2/2) is already in a register -- and that dgrad then uses
+ *   MUL_AUX (v *= aux[m,n], one multiply) instead of MUL_DGELU (v *= gelu_erf'(aux[m,n]), ~17 instructions per element in an
+ *   epilogue that is issue-bound).
  *   ATOMIC: fp32 red.add into out (split-K wgrad accumulation; out must be pre-zeroed or hold the running sum).
  * ------------------------------------------------------------------------------------------------------------ */
 #define MERLOT_GEMM_OUT_F32 1u
@@ -61,6 +64,8 @@ void merlot_reset_launch_count(void);
 #define MERLOT_GEMM_GELU 4u
 #define MERLOT_GEMM_MUL_DGELU 8u
 #define MERLOT_GEMM_DROPOUT 16u
+#define MERLOT_GEMM_GELU_GRAD_OUT 32u
+#define MERLOT_GEMM_MUL_AUX 64u
 
 typedef struct merlot_gemm {
   int M, N, K;
@@ -70,7 +75,7 @@ typedef struct merlot_gemm {
   void* out2; int ld_out2;        /* optional second bf16 output (post-GELU) */
   const float* bias;              /* [N] fp32 or NULL */
   const void* resid; int ld_resid;/* bf16 [M,N] or NULL */
-  const void* aux; int ld_aux;    /* bf16 [M,N] pre-activation for MUL_DGELU */
+  const void* aux; int ld_aux;    /* bf16 [M,N]: pre-activation for MUL_DGELU / the saved factor for MUL_AUX */
   float alpha;
   uint32_t flags;
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;

@@ -22,6 +22,8 @@ GEMM_ATOMIC = 2
 GEMM_GELU = 4
 GEMM_MUL_DGELU = 8
 GEMM_DROPOUT = 16
+GEMM_GELU_GRAD_OUT = 32
+GEMM_MUL_AUX = 64
 
 
 class MerlotError(RuntimeError):

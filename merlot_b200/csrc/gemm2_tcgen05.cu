@@ -285,6 +285,8 @@ static int launch_gemm2_mn(int epi, int fl, const CUtensorMap& ta, const CUtenso
     case F_BIAS: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS>(ta, tb, p, grid, stream);
     case F_BIAS | F_GELU | F_DUAL: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL>(ta, tb, p, grid, stream);
     case F_DGELU: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_DGELU>(ta, tb, p, grid, stream);
+    case F_BIAS | F_GELU | F_DUAL | F_GRADOUT: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL | F_GRADOUT>(ta, tb, p, grid, stream);
+    case F_MULAUX: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_MULAUX>(ta, tb, p, grid, stream);
     case F_BIAS | F_RESID: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID>(ta, tb, p, grid, stream);
     case F_BIAS | F_RESID | F_DROP: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID | F_DROP>(ta, tb, p, grid, stream);
     case F_RESID: return launch_gemm2_inst<BN, A_MN, B_MN, 1, F_RESID>(ta, tb, p, grid, stream);

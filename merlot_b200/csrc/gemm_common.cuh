@@ -65,7 +65,16 @@ __device__ __forceinline__ void epi_math8(const GemmDev& p, int row, int col, bo
   }
   if (p.flags & MERLOT_GEMM_GELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { pre[i] = v[i]; v[i] = gelu_erf_fast(v[i]); }
+    for (int i = 0; i < 8; ++i) {
+      pre[i] = (p.flags & MERLOT_GEMM_GELU_GRAD_OUT) ? gelu_erf_grad_fast(v[i]) : v[i];
+      v[i] = gelu_erf_fast(v[i]);
+    }
+  }
+  if ((p.flags & MERLOT_GEMM_MUL_AUX) && in_range) {
+    const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (col + i < p.N) v[i] *= __bfloat162float(a[i]);
   }
   if ((p.flags & MERLOT_GEMM_MUL_DGELU) && in_range) {
     const bf16* a = p.aux + (size_t)row * p.ld_aux + col;
@@ -153,11 +162,12 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // Epilogue feature masks.  The staged epilogue is instantiated once per feature set that the model uses (plus one generic,
 // run-time-flag instance): with one generic body the plain path hops over the gelu / dropout / residual blocks and spends
 // most of its time in instruction-cache misses (ncu: stall_no_inst on every BSSY/BSYNC of the skipped blocks).
-enum : int { F_ALPHA = 1, F_BIAS = 2, F_GELU = 4, F_DUAL = 8, F_DGELU = 16, F_DROP = 32, F_RESID = 64, F_GENERIC = -1 };
+enum : int { F_ALPHA = 1, F_BIAS = 2, F_GELU = 4, F_DUAL = 8, F_DGELU = 16, F_DROP = 32, F_RESID = 64, F_GRADOUT = 128, F_MULAUX = 256, F_GENERIC = -1 };
 __device__ __forceinline__ int epi_features(const GemmDev& p) {
   return (p.alpha != 1.0f ? F_ALPHA : 0) | (p.bias ? F_BIAS : 0) | ((p.flags & MERLOT_GEMM_GELU) ? F_GELU : 0) |
          (((p.flags & MERLOT_GEMM_GELU) && p.out2) ? F_DUAL : 0) | ((p.flags & MERLOT_GEMM_MUL_DGELU) ? F_DGELU : 0) |
-         ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0);
+         ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0) |
+         ((p.flags & MERLOT_GEMM_GELU_GRAD_OUT) ? F_GRADOUT : 0) | ((p.flags & MERLOT_GEMM_MUL_AUX) ? F_MULAUX : 0);
 }
 template <int FL>
 __device__ __forceinline__ bool feat(int run_time_features, int f) { return FL == F_GENERIC ? (run_time_features & f) != 0 : (FL & f) != 0; }
@@ -177,16 +187,34 @@ __device__ __forceinline__ void epi_math8_regs(const GemmDev& p, int rtf, int ro
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
   if (feat<FL>(rtf, F_GELU)) {
+    if (feat<FL>(rtf, F_GRADOUT)) {  // first output = gelu'(pre) (the FFN2 dgrad's factor), second = gelu(pre): Phi and exp shared
 #pragma unroll
-    for (int k = 0; k < 4; ++k) pre_packed[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+      for (int k = 0; k < 4; ++k) {
+        float e0, e1;
+        const float x0 = v[2 * k], x1 = v[2 * k + 1];
+        const float c0 = normal_cdf_fast(x0, &e0), c1 = normal_cdf_fast(x1, &e1);
+        pre_packed[k] = pack_bf16x2(fmaf(x0 * 0.39894228040143267794f, e0, c0), fmaf(x1 * 0.39894228040143267794f, e1, c1));
+        v[2 * k] = x0 * c0;
+        v[2 * k + 1] = x1 * c1;
+      }
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = gelu_erf_fast(v[k]);
+      for (int k = 0; k < 4; ++k) pre_packed[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = gelu_erf_fast(v[k]);
+    }
   }
   if (feat<FL>(rtf, F_DGELU)) {  // companion = gelu' input
     float a[8];
     unpack8(compq, a);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] *= gelu_erf_grad_fast(a[k]);
+  }
+  if (feat<FL>(rtf, F_MULAUX)) {  // companion = the saved factor
+    float a[8];
+    unpack8(compq, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= a[k];
   }
   if (feat<FL>(rtf, F_DROP)) {
     const uint64_t lin = (uint64_t)row * (uint64_t)p.N + (uint64_t)col;  // col % 8 == 0, N % 8 == 0 enforced on host
@@ -276,8 +304,8 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmDev& p, int rtf, int
     const int c = n0 + plan.tcol_of(0) + lane;
     cy.bnext = c < p.N ? __ldg(p.bias + c) : 0.0f;
   }
-  if (plan.wide && (feat<FL>(rtf, F_DGELU) || feat<FL>(rtf, F_RESID))) {
-    const bool dg = feat<FL>(rtf, F_DGELU);
+  if (plan.wide && (feat<FL>(rtf, F_DGELU) || feat<FL>(rtf, F_MULAUX) || feat<FL>(rtf, F_RESID))) {
+    const bool dg = feat<FL>(rtf, F_DGELU) || feat<FL>(rtf, F_MULAUX);
     comp_fetch(dg ? p.aux : p.resid, dg ? p.ld_aux : p.ld_resid, row0q, n0 + plan.tcol_of(0), p.M, p.N, lane, cy.cp);
   }
 }
@@ -299,7 +327,7 @@ __device__ __forceinline__ void epilogue_tile_loop(const GemmDev& p, int rtf, ui
   const int my_chunks = plan.my_chunks;
   const int row = row0q + lane;
   const bool in_range = row < p.M;
-  const bool do_dgelu = feat<FL>(rtf, F_DGELU);
+  const bool do_dgelu = feat<FL>(rtf, F_DGELU) || feat<FL>(rtf, F_MULAUX);  // the companion operand is p.aux
   const bf16* comp = !wide ? nullptr : do_dgelu ? p.aux : (feat<FL>(rtf, F_RESID) ? p.resid : nullptr);
   const int ld_comp = do_dgelu ? p.ld_aux : p.ld_resid;
   const bf16* resid2 = ((!wide || do_dgelu) && feat<FL>(rtf, F_RESID)) ? p.resid + (size_t)row * p.ld_resid : nullptr;  // rare: unprefetched

@@ -238,7 +238,7 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
 // Feature sets with a dedicated epilogue instance (everything else runs the generic, run-time-flag instance).
 __host__ inline int epi_specialised(int fl) {
   switch (fl) {
-    case 0: case F_BIAS: case F_BIAS | F_GELU | F_DUAL: case F_DGELU: case F_BIAS | F_RESID | F_DROP: case F_BIAS | F_RESID: case F_RESID: return fl;
+    case 0: case F_BIAS: case F_BIAS | F_GELU | F_DUAL: case F_BIAS | F_GELU | F_DUAL | F_GRADOUT: case F_MULAUX: case F_DGELU: case F_BIAS | F_RESID | F_DROP: case F_BIAS | F_RESID: case F_RESID: return fl;
     default: return F_GENERIC;
   }
 }
@@ -252,6 +252,8 @@ static int launch_gemm_mn(int epi, int fl, const CUtensorMap& ta, const CUtensor
     case F_BIAS: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_BIAS>(ta, tb, p, grid, stream);
     case F_BIAS | F_GELU | F_DUAL: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL>(ta, tb, p, grid, stream);
     case F_DGELU: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_DGELU>(ta, tb, p, grid, stream);
+    case F_BIAS | F_GELU | F_DUAL | F_GRADOUT: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_BIAS | F_GELU | F_DUAL | F_GRADOUT>(ta, tb, p, grid, stream);
+    case F_MULAUX: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_MULAUX>(ta, tb, p, grid, stream);
     case F_BIAS | F_RESID: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID>(ta, tb, p, grid, stream);
     case F_BIAS | F_RESID | F_DROP: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_BIAS | F_RESID | F_DROP>(ta, tb, p, grid, stream);
     case F_RESID: return launch_gemm_inst<BN, A_MN, B_MN, 1, F_RESID>(ta, tb, p, grid, stream);

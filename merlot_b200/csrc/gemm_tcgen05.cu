@@ -63,7 +63,10 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
              "gemm: leading dimension smaller than the row length");
   const bool out_f32 = g->flags & MERLOT_GEMM_OUT_F32;
   MB_REQUIRE(!(g->flags & MERLOT_GEMM_ATOMIC) || out_f32, MERLOT_EINVAL, "gemm: ATOMIC requires OUT_F32");
-  MB_REQUIRE(!(g->flags & MERLOT_GEMM_MUL_DGELU) || g->aux, MERLOT_EINVAL, "gemm: MUL_DGELU requires aux");
+  MB_REQUIRE(!(g->flags & (MERLOT_GEMM_MUL_DGELU | MERLOT_GEMM_MUL_AUX)) || g->aux, MERLOT_EINVAL, "gemm: MUL_DGELU / MUL_AUX require aux");
+  MB_REQUIRE(!((g->flags & MERLOT_GEMM_MUL_DGELU) && (g->flags & MERLOT_GEMM_MUL_AUX)), MERLOT_EINVAL, "gemm: MUL_DGELU and MUL_AUX are exclusive");
+  MB_REQUIRE(!(g->flags & MERLOT_GEMM_GELU_GRAD_OUT) || ((g->flags & MERLOT_GEMM_GELU) && g->out2), MERLOT_EINVAL,
+             "gemm: GELU_GRAD_OUT needs GELU and out2");
   MB_REQUIRE(g->ld_out >= g->N, MERLOT_ESHAPE, "gemm: ld_out < N");
   if (!out_f32)
     MB_REQUIRE((g->ld_out % 8) == 0 && ((uintptr_t)g->out % 16) == 0, MERLOT_ESHAPE,
@@ -161,12 +164,13 @@ extern "C" int merlot_gemm_bf16(const merlot_gemm_t* g, void* stream_) {
 
   // epilogue route: 1 = bf16 tiles through swizzled smem staging + TMA store; 2 = fp32 split-K accumulation through TMA
   // reduce-add (plain alpha*acc only); 0 = direct register->global stores (other fp32 outputs)
-  const bool plain = !g->bias && !g->resid && !(g->flags & (MERLOT_GEMM_GELU | MERLOT_GEMM_MUL_DGELU | MERLOT_GEMM_DROPOUT));
+  const bool plain = !g->bias && !g->resid && !(g->flags & (MERLOT_GEMM_GELU | MERLOT_GEMM_MUL_DGELU | MERLOT_GEMM_MUL_AUX | MERLOT_GEMM_DROPOUT));
   const int epi = !out_f32 ? 1
                   : ((g->flags & MERLOT_GEMM_ATOMIC) && plain && (g->ld_out % 4) == 0 && ((uintptr_t)g->out % 16) == 0) ? 2 : 0;
   const int fl = (p.alpha != 1.0f ? F_ALPHA : 0) | (p.bias ? F_BIAS : 0) | ((p.flags & MERLOT_GEMM_GELU) ? F_GELU : 0) |
                  (((p.flags & MERLOT_GEMM_GELU) && p.out2) ? F_DUAL : 0) | ((p.flags & MERLOT_GEMM_MUL_DGELU) ? F_DGELU : 0) |
-                 ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0);
+                 ((p.flags & MERLOT_GEMM_DROPOUT) ? F_DROP : 0) | (p.resid ? F_RESID : 0) |
+                 ((p.flags & MERLOT_GEMM_GELU_GRAD_OUT) ? F_GRADOUT : 0) | ((p.flags & MERLOT_GEMM_MUL_AUX) ? F_MULAUX : 0);
   if (epi == 1 && (g->flags & MERLOT_GEMM_GELU) && g->out2)
     MB_REQUIRE(((uintptr_t)g->out2 % 16) == 0, MERLOT_ESHAPE, "gemm: out2 must be 16-byte aligned");
   if (pair) return launch_gemm_pair(bn, g->a_mn_major != 0, g->b_mn_major != 0, epi, fl, ta, tb, p, grid, stream);

@@ -166,6 +166,7 @@ extern "C" int merlot_stack_forward(const merlot_stack_t* s, void* stream_) {
     {
       merlot_gemm_t e = gemm_base(0, 0, 0);
       e.out = A.pre; e.ld_out = I; e.out2 = A.act; e.ld_out2 = I; e.flags = MERLOT_GEMM_GELU;
+      if (s->save_for_backward) e.flags |= MERLOT_GEMM_GELU_GRAD_OUT;  // `pre` then holds gelu'(pre): all the backward needs of it
       RC(linear_fwd(A.x2, H, P.w_1, I, P.b_1, M, e, st));
     }
     {
@@ -240,7 +241,7 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
     RC(linear_wgrad(A.act, I, d, H, P.g_w_2, M, st));
     {
       merlot_gemm_t e = gemm_base(0, 0, 0);
-      e.flags = MERLOT_GEMM_MUL_DGELU; e.aux = A.pre; e.ld_aux = I;
+      e.flags = MERLOT_GEMM_MUL_AUX; e.aux = A.pre; e.ld_aux = I;  // A.pre = gelu'(pre), saved by the forward epilogue
       RC(linear_dgrad(d, H, P.w_2, I, dpre, M, e, st));
     }
     // ---- FFN1 ----

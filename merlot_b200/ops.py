@@ -27,6 +27,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
          gelu: bool = False, out_pre: Optional[torch.Tensor] = None, dgelu_aux: Optional[torch.Tensor] = None,
+         gelu_grad_out: bool = False, mul_aux: Optional[torch.Tensor] = None,
          alpha: float = 1.0, atomic: bool = False, dropout_p: float = 0.0, dropout_seed: int = 0,
          dropout_site: int = 0, splits: int = 0, block_n: int = 0,
          M: Optional[int] = None, N: Optional[int] = None, K: Optional[int] = None) -> torch.Tensor:
@@ -35,7 +36,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     a: [M,K] (or [K,M] when a_mn_major); b: [N,K] (or [K,N] when b_mn_major); both bf16, row-major, 2-D.
     With gelu=True and out_pre given: out_pre <- pre-activation, return value <- gelu(pre).
     """
-    _require_cuda(a, b, out, bias, resid, out_pre, dgelu_aux)
+    _require_cuda(a, b, out, bias, resid, out_pre, dgelu_aux, mul_aux)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1
     if M is None:
@@ -70,6 +71,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if dgelu_aux is not None:
         flags |= L.GEMM_MUL_DGELU
         g.aux, g.ld_aux = dgelu_aux.data_ptr(), dgelu_aux.stride(0)
+    if gelu_grad_out:  # out_pre receives gelu'(pre) instead of pre
+        assert gelu and out_pre is not None
+        flags |= L.GEMM_GELU_GRAD_OUT
+    if mul_aux is not None:  # v *= aux (the factor saved by gelu_grad_out)
+        assert dgelu_aux is None
+        flags |= L.GEMM_MUL_AUX
+        g.aux, g.ld_aux = mul_aux.data_ptr(), mul_aux.stride(0)
     if bias is not None:
         assert bias.dtype == torch.float32
         g.bias = bias.data_ptr()

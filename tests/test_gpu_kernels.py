@@ -62,6 +62,14 @@ def test_gemm_epilogues(ops):
     x = aux.float().requires_grad_(True)
     O.gelu(x).sum().backward()
     assert rel(ops.gemm(ad, wd, b_mn_major=True, dgelu_aux=aux.to(DEV)), (a.float() @ w.float()) * x.grad) < 6e-3
+    # the pair the stacks use: the forward saves gelu'(pre) (GELU_GRAD_OUT), the FFN2 dgrad multiplies by it (MUL_AUX)
+    for kw in (dict(), dict(block_n=128), dict(block_n=256)):
+        gsave = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        act2 = ops.gemm(ad, wd, b_mn_major=True, bias=bd, gelu=True, out_pre=gsave, gelu_grad_out=True, **kw)
+        xb = base.clone().requires_grad_(True)
+        O.gelu(xb).sum().backward()
+        assert rel(act2, O.gelu(base)) < 6e-3 and rel(gsave, xb.grad) < 6e-3
+        assert rel(ops.gemm(ad, wd, b_mn_major=True, mul_aux=gsave, **kw), (a.float() @ w.float()) * gsave.float().cpu()) < 6e-3
     dy = (torch.randn(M, N, generator=g) * 0.1).bfloat16()
     dw = torch.zeros(K, N, dtype=torch.float32, device=DEV)
     for _ in range(2):  # accumulation semantics of the flat gradient arena (shared `encoder` weights get two passes)
