@@ -289,6 +289,30 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     log("e2e region done")
 
+    # ---- data-parallel diagnostics: per-rank device time of the timed region, and the step time WITHOUT the gradient
+    # all-reduce (same kernels, collective skipped) = what the collective costs after overlap ----
+    dp_info = None
+    if dist is not None:
+        mine = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        allms = [torch.empty_like(mine) for _ in range(world)]
+        dist.dist.all_gather(allms, mine)
+        dist.skip_grad_allreduce = True
+        one_step(feats)
+        sync_all()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(5):
+            one_step(feats)
+        n1.record()
+        sync_all()
+        dist.skip_grad_allreduce = False
+        nc = torch.tensor([n0.elapsed_time(n1) / 5], device=dev)
+        dist.dist.all_reduce(nc, op=dist.dist.ReduceOp.MAX)
+        dp_info = {"per_rank_ms_per_step": [round(float(x), 3) for x in allms], "ms_per_step_without_grad_allreduce": float(nc),
+                   "grad_allreduce_exposed_ms": ms_total / args.steps - float(nc), "grad_bytes_fp32": int(store.g.numel() * 4),
+                   "buckets": "1 (everything outside the ViT, under the ViT backward) + 4 ViT layer groups top-down",
+                   "note": "runs after both timed regions; the replicas parameters differ afterwards (only the single-rank roofline step follows)"}
+
     # ---- roofline of the dominant kernel (K1 GEMM), one extra step with per-launch CUDA events ----
     roof = None
     # the profiled step runs with the language-only stack serialised on the main stream: with two streams sharing the SMs a
@@ -348,6 +372,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": roof,
             "attention": attn,
+            "data_parallel": dp_info,
             "cpu_baseline": cpu,
             "loss": loss_val, "loss_e2e_last_step": loss_e2e,
         }

@@ -31,6 +31,9 @@ extern "C" {
 #define MERLOT_ECUDA (-3)    /* CUDA runtime / driver error */
 #define MERLOT_ENOTIMPL (-4) /* config key accepted by the reference but not yet provided here (raised loudly) */
 
+/* Leave n SMs to concurrently running collectives (NCCL gradient all-reduce): the persistent kernels (K1, K3) size their grids to
+ * (SM count - n) so that none of their CTAs has to queue behind a collective's CTA.  0 = use every SM (single-GPU default). */
+void merlot_set_sm_reserve(int n);
 const char* merlot_last_error(void);
 int merlot_abi_version(void);
 /* number of kernels this library has launched since the last reset (bench.py reports it as gpu_launches) */

@@ -22,6 +22,11 @@ int set_error(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_sm_reserve{0};
+
+// SMs the persistent kernels (K1, K3) may fill.  With data parallelism NCCL's collective CTAs each occupy a whole SM for
+// milliseconds; a persistent kernel launched with one CTA per SM then has CTAs that cannot start until others have finished
+// and, with a static tile schedule, takes up to twice as long.  merlot_set_sm_reserve(n) leaves n SMs to the collective.
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -29,7 +34,8 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  return sms;
+  const int r = g_sm_reserve.load(std::memory_order_relaxed);
+  return (r > 0 && r < sms - 8) ? sms - r : sms;
 }
 
 // cuTensorMapEncodeTiled is a driver-API symbol; resolve it through the runtime so the library has no link-time
@@ -88,6 +94,7 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 
 }  // namespace mb
 
+extern "C" void merlot_set_sm_reserve(int n) { mb::g_sm_reserve.store(n < 0 ? 0 : n); }
 extern "C" const char* merlot_last_error(void) { return mb::last_error_buf(); }
 extern "C" int merlot_abi_version(void) { return 1; }
 extern "C" long long merlot_launch_count(void) { return mb::g_launches.load(); }

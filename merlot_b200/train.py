@@ -30,20 +30,39 @@ class DataParallel:
     def __init__(self, backend: Optional[str] = None):
         import torch.distributed as dist
         self.dist = dist
+        # The gradient all-reduce runs under the backward pass: bound the SMs NCCL may take (one collective CTA owns a whole SM)
+        # and keep the persistent GEMM / attention grids off those SMs (merlot_set_sm_reserve) -- otherwise every persistent
+        # kernel launched while a collective is in flight has CTAs queueing behind NCCL's and runs up to twice as long.
+        self.comm_ctas = int(os.environ.get("MERLOT_DP_COMM_CTAS", "24"))
+        if self.comm_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(self.comm_ctas))
+            os.environ.setdefault("NCCL_MIN_CTAS", str(min(4, self.comm_ctas)))
         if not dist.is_initialized():
             dist.init_process_group(backend=backend or ("nccl" if torch.cuda.is_available() else "gloo"))
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
+        self._lib = None
+        if self.world > 1 and self.comm_ctas > 0 and torch.cuda.is_available():
+            from . import _lib
+            self._lib = _lib.lib()
+
+    def reserve_sms(self, on: bool):
+        """Kernels ENQUEUED while this is on leave `comm_ctas` SMs to the collective (train_op switches it on for the part of
+        the backward pass that runs under the gradient all-reduce)."""
+        if self._lib is not None:
+            self._lib.merlot_set_sm_reserve(self.comm_ctas if on else 0)
 
     def all_reduce_grads(self, g: torch.Tensor):
         """Sum over replicas; the 1/world of the MEAN reduction is folded into the AdamW kernel (grad_scale)."""
         if self.world > 1:
             self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM)
 
+    skip_grad_allreduce = False  # diagnostics only (bench.py: step time without the gradient collective = its exposed cost)
+
     def all_reduce_ranges_async(self, g: torch.Tensor, ranges):
         """Start summing g[a:b] for every range on the NCCL stream, ordered after the work already queued on the current
         stream; returns handles for wait_all().  Lets the collective overlap the rest of the backward pass."""
-        if self.world <= 1:
+        if self.world <= 1 or self.skip_grad_allreduce:
             return []
         return [self.dist.all_reduce(g[a:b], op=self.dist.ReduceOp.SUM, async_op=True) for a, b in ranges if b > a]
 
@@ -164,8 +183,12 @@ def model_fn_builder(config: NeatConfig, *, store: Optional[ParamStore] = None, 
                     if k + 1 < len(groups):
                         vit_pending.append(dist.all_reduce_ranges_async(store.g, vit_ranges[k]))
 
-                model.backward(on_non_vit_grads_ready=lambda: pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges)),
-                               vit_layer_groups=groups, on_vit_group_done=on_group)
+                def on_rest():
+                    pending.extend(dist.all_reduce_ranges_async(store.g, store.rest_ranges))
+                    dist.reserve_sms(True)  # the ViT backward is enqueued (and runs) under the collectives
+
+                model.backward(on_non_vit_grads_ready=on_rest, vit_layer_groups=groups, on_vit_group_done=on_group)
+                dist.reserve_sms(False)
                 vit_pending.append(dist.all_reduce_ranges_async(store.g, vit_ranges[-1]))
                 dist.wait_all(pending)
                 optimizer.apply_gradients(grad_scale=1.0 / world, skip=skip, zero_grad=True, only=store.rest_ranges, advance=False)
