@@ -134,6 +134,9 @@ void merlot_attention_debug_mode(int mode);
 int merlot_attention_bwd_dq_parts(int S);                          /* slices used by bwd for this S; 0 = atomic single slice */
 size_t merlot_attention_bwd_workspace_bytes(int B, int S, int heads); /* bytes of dq_accum (ld_dq = heads*64) */
 int merlot_attention_colsum(const merlot_attn_t* a, void* stream);
+/* Export path (PREDICT): probs_bss f32 [B,S,S] <- head-mean probabilities of this layer = one layer of `self_attn_probs`
+ * (utils/transformer.py:208-209,238 with compress_attn=True), recomputed from qkv + lse. */
+int merlot_attention_probs(const merlot_attn_t* a, float* probs_bss, void* stream);
 /* attention_log (model/modeling.py:186-203): out4 = {lang2lang, lang2viz, viz2lang, viz2viz} normalised block sums of the
  * layer/head/batch-mean attention map, from the two split column sums (queries in the viz piece / in the lang piece). */
 int merlot_attention_log_blocks(const float* c_viz, const float* c_lang, const void* valid_u8, int B, int S, int P, float* out4,
@@ -238,6 +241,7 @@ typedef struct merlot_stack {
   float hidden_dropout_p; float attention_dropout_p; uint64_t dropout_seed; uint32_t dropout_site_base;
   float* attn_colsum;                          /* optional f32 [B,S]: += sum over layers,queries of head-mean probs */
   float* attn_colsum2; int attn_colsum_split; int attn_colsum_valid_q;  /* optional split by query piece (attention_log) */
+  float* attn_probs;                           /* optional f32 [layers][B,S,S]: head-mean probabilities of every layer (export) */
   /* backward */
   const void* dy;                              /* bf16 [B*S, H] gradient wrt y */
   void* dh_in;                                 /* bf16 [B*S, H] gradient wrt h_in (optional) */

@@ -164,6 +164,7 @@ class StackDesc(C.Structure):
         ("dropout_site_base", C.c_uint32),
         ("attn_colsum", C.c_void_p),
         ("attn_colsum2", C.c_void_p), ("attn_colsum_split", C.c_int), ("attn_colsum_valid_q", C.c_int),
+        ("attn_probs", C.c_void_p),
         ("dy", C.c_void_p),
         ("dh_in", C.c_void_p),
         ("scratch", C.c_void_p),

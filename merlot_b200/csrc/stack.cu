@@ -152,6 +152,7 @@ extern "C" int merlot_stack_forward(const merlot_stack_t* s, void* stream_) {
         a.colsum2 = s->attn_colsum2; a.colsum_split = s->attn_colsum_split; a.colsum_valid_q = s->attn_colsum_valid_q;
         RC(merlot_attention_colsum(&a, st));
       }
+      if (s->attn_probs) RC(merlot_attention_probs(&a, s->attn_probs + (size_t)l * s->B * s->S * s->S, st));
     }
     {
       merlot_gemm_t e = gemm_base(0, 0, 0);

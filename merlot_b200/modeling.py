@@ -86,7 +86,7 @@ class _Stack:
     """One transformer stack invocation (utils/transformer.py:171-247) through merlot_stack_forward/backward."""
 
     def __init__(self, store, bufs, tag, scope, layers, B, S, valid, h_in, cfg, dropout_p, seed, site, save, colsum=None,
-                 colsum2=None, colsum_split=0, colsum_valid_q=0):
+                 colsum2=None, colsum_split=0, colsum_valid_q=0, probs=None):
         H, I, heads = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_attention_heads"]
         if H % heads != 0 or H // heads != 64:
             raise ValueError("passed in a tensor of shape {} when size_per_head={} and num_attention_heads={}".format(
@@ -111,7 +111,8 @@ class _Stack:
         d.attn_colsum = colsum.data_ptr() if colsum is not None else None
         d.attn_colsum2 = colsum2.data_ptr() if colsum2 is not None else None
         d.attn_colsum_split, d.attn_colsum_valid_q = int(colsum_split), int(colsum_valid_q)
-        self.d, self.bufs, self.tag, self.keep = d, bufs, tag, (valid, h_in, colsum)
+        d.attn_probs = probs.data_ptr() if probs is not None else None
+        self.d, self.bufs, self.tag, self.keep = d, bufs, tag, (valid, h_in, colsum, probs)
 
     def forward(self):
         L.check(L.lib().merlot_stack_forward(C.byref(self.d), ops._stream()))
@@ -141,7 +142,7 @@ class MerlotModel(object):
     def __init__(self, config, is_training, use_tpu, image, input_ids, mask_input=False, shuffled_idx_img=None,
                  img_mask=None, log_attention_probs=True, *, params: ParamStore, mask_draws: Optional[Dict] = None,
                  mask_override: Optional[Dict] = None, dropout_seed: int = 0, save_for_backward: Optional[bool] = None,
-                 dist=None):
+                 dist=None, export_attention_probs: bool = False):
         """Arguments as model/modeling.py:48-66.  `use_tpu` is accepted and ignored (it only selects one-hot vs gather
         embedding lookups in the reference, utils/model_utils.py:259-263 -- same values either way)."""
         self.config = copy.deepcopy(config)
@@ -154,8 +155,11 @@ class MerlotModel(object):
             raise L.MerlotError(L.MERLOT_EINVAL, "MerlotModel needs CUDA tensors: merlot_b200 has no CPU fallback")
         if not cfg.get("use_bfloat16", False):
             raise NotImplementedError("use_bfloat16: False (fp32 activations) is not provided; every shipped config sets True")
-        if cfg.get("num_imgs", 1) != 1 or cfg.get("num_texts", 1) != 1 or img_mask is not None:
-            raise NotImplementedError("num_imgs / num_texts / img_mask (VCR path, model/modeling.py:106-122) not provided yet")
+        if cfg.get("num_imgs", 1) != 1 or img_mask is not None:
+            raise NotImplementedError("num_imgs > 1 / img_mask (model/modeling.py:106-122) not provided (no shipped config uses them)")
+        if cfg.get("num_texts", 1) > 1 and (mask_input or shuffled_idx_img is not None):
+            raise NotImplementedError("num_texts > 1 (VCR, model/modeling.py:111-119) is a finetuning/inference path: mask_input and "
+                                      "shuffled_idx_img are not combined with it in the reference either (:319-320)")
         if cfg.get("disable_pairwise_lang_attn", False):
             raise NotImplementedError("disable_pairwise_lang_attn (model/modeling.py:160-168) not provided yet")
         if not cfg.get("share_params", True):
@@ -186,6 +190,9 @@ class MerlotModel(object):
         self._bufs = _Buffers(params)
         self._mask_input = mask_input
         self._log_attention_probs = log_attention_probs
+        # PREDICT-mode outputs of model_fn (model/modeling.py:762-770): encoder_info / lang_transformer_info['self_attn_probs']
+        # = head-mean probabilities [B, layers, S, S].  Materialised only on request (60 MB per joint layer at configs[1]).
+        self._export_probs = bool(export_attention_probs)
         self._forward(image, shuffled_idx_img, mask_draws, mask_override)
 
     # ---- shapes (:226-260) ----
@@ -237,8 +244,9 @@ class MerlotModel(object):
         assert w0 % Pp == 0  # :190
         if c3 != 3:
             raise ValueError(f"image must be [N,h,w,3], got {tuple(image.shape)}")
-        if N != self.batch_size * self.num_chunks:
-            raise ValueError(f"image batch {N} != batch_size*num_chunks {self.batch_size * self.num_chunks}")
+        nt = self.num_texts
+        if N * nt != self.batch_size * self.num_chunks:
+            raise ValueError(f"image batch {N} x num_texts {nt} != batch_size*num_chunks {self.batch_size * self.num_chunks}")
         ncls = cfg.get("num_cls_emb", 2)
         h1, w1 = h0 // Pp, w0 // Pp
         np_ = h1 * w1
@@ -294,7 +302,7 @@ class MerlotModel(object):
         # ---- viz tokens (:95-133) ----
         if shuffled_idx_img is None:
             img_idx = bf.get("img_idx.arange", (N,), torch.int32)
-            img_idx.copy_(torch.arange(ncg, dtype=torch.int32, device=dev).repeat(B))
+            img_idx.copy_(torch.arange(ncg, dtype=torch.int32, device=dev).repeat(B // nt))
             self._shuffled = None
         else:
             assert self.num_imgs == 1 and self.num_texts == 1  # :319-320
@@ -302,14 +310,16 @@ class MerlotModel(object):
             if img_idx.numel() != N:
                 raise ValueError(f"shuffled_idx_img has {img_idx.numel()} entries, expected B*num_chunks_in_group = {N}")
         self._img_idx = img_idx
-        xsum_z = bf.get("viz.xsum", (B * Pz, H), torch.float32)
+        Bi = B // nt  # image groups; with num_texts > 1 every group's tokens are tiled to its nt texts (model/modeling.py:111-119)
+        xsum_z = bf.get("viz.xsum", (Bi * Pz, H), torch.float32)
         self.img_trg_h = bf.get("viz.img_trg", (N, H), torch.float32)
         ops.viz_assemble_fwd(hv, st.P("vision_backbone/img_idx_pe"), img_idx, st.P("vision_backbone/final_pe/pos_embs"),
                              st.P("vision_backbone/final_pe/cls_emb"), xsum_z, self.img_trg_h, N, h1, w1, ncls, max(sp, 1), H)
         joint_in = bf.get("joint.in", (B * Sj, H), torch.bfloat16)
-        mean_z, rstd_z = bf.get("viz.mean", (B * Pz,), torch.float32), bf.get("viz.rstd", (B * Pz,), torch.float32)
-        ops.layernorm_fwd(xsum_z, joint_in, st.P("vision_backbone/LayerNorm_final_ln/gamma"),
-                          st.P("vision_backbone/LayerNorm_final_ln/beta"), mean_z, rstd_z, remap=(Pz, Sj, 0))
+        mean_z, rstd_z = bf.get("viz.mean", (Bi * Pz,), torch.float32), bf.get("viz.rstd", (Bi * Pz,), torch.float32)
+        for j in range(nt):  # image group g feeds joint rows of texts g*nt + j: row remap (group stride nt*Sj, offset j*Sj)
+            ops.layernorm_fwd(xsum_z, joint_in, st.P("vision_backbone/LayerNorm_final_ln/gamma"),
+                              st.P("vision_backbone/LayerNorm_final_ln/beta"), mean_z, rstd_z, rows=Bi * Pz, remap=(Pz, nt * Sj, j * Sj))
 
         # ---- language-only encoder + masking (:135-139) ----
         ids_bl = self.input_ids.reshape(B, Lj)
@@ -333,9 +343,12 @@ class MerlotModel(object):
         if self._log_attention_probs:  # split column sums of the joint attention maps for attention_log (:186-203)
             c_viz = bf.get("joint.c_viz", (B * Sj,), torch.float32, zero=True)
             c_lang = bf.get("joint.c_lang", (B * Sj,), torch.float32, zero=True)
+        probs_j = None
+        if self._export_probs:
+            probs_j = bf.get("joint.probs", (cfg["num_hidden_layers"], B, Sj, Sj), torch.float32)
         self._joint = _Stack(st, bf, "joint", "encoder", cfg["num_hidden_layers"], B, Sj, valid_j, joint_in, cfg,
                              p_hid if train else 0.0, self._seed, _SITE_JOINT, self._save, colsum=c_viz, colsum2=c_lang,
-                             colsum_split=Pz, colsum_valid_q=1)
+                             colsum_split=Pz, colsum_valid_q=1, probs=probs_j)
         self._y_j = self._joint.forward()
         self._attn_log = None
         if self._log_attention_probs:
@@ -345,6 +358,8 @@ class MerlotModel(object):
                                                         ops._stream()))
             self._attn_log = out4
         self.encoder_info = {"hidden_state": self._y_j.view(B, Sj, H)}
+        if probs_j is not None:  # [layers,B,S,S] -> the reference's [B, layers, S, S] (utils/transformer.py:238), a view
+            self.encoder_info["self_attn_probs"] = probs_j.permute(1, 0, 2, 3)
         self._hidden_f32 = {}
         self.encoder_pieces = [{"name": "viz", "start": 0, "end": Pz}, {"name": "lang", "start": Pz, "end": Sj}]
         self._heads = {}
@@ -570,8 +585,11 @@ class MerlotModel(object):
         ops.ids_valid(ids, valid)
         summ = bf.get("lo.attn_summ", (Blo * Llo,), torch.float32, zero=True)
         p = float(self.dropout_prob or 0.0) if self.is_training else 0.0
+        probs_lo = None
+        if self._export_probs:
+            probs_lo = bf.get("lo.probs", (cfg["num_lang_transformer_hidden_layers"], Blo, Llo, Llo), torch.float32)
         self._lo = _Stack(st, bf, "lo", "encoder", cfg["num_lang_transformer_hidden_layers"], Blo, Llo, valid, h0, cfg, p,
-                          self._seed, _SITE_LANGONLY, self._save, colsum=summ)
+                          self._seed, _SITE_LANGONLY, self._save, colsum=summ, probs=probs_lo)
         y = self._lo.forward()
         nch = self.batch_size * self.num_chunks
         pool_idx = bf.get("lo.pool_idx", (nch,), torch.int32)
@@ -581,6 +599,8 @@ class MerlotModel(object):
         ops.gather_rows(y, pool_idx, self.lang_trg_h)
         # attention_summs of mask_inputs (:428-431): sum over (layers, queries) of head-mean probabilities, as [B, L]
         self.lang_transformer_info = {"hidden_state": y.view(Blo, Llo, H), "attention_summs": summ.view(self.B, self.L)}
+        if probs_lo is not None:
+            self.lang_transformer_info["self_attn_probs"] = probs_lo.permute(1, 0, 2, 3)
         return self.lang_trg_h, self.lang_transformer_info
 
     def langonly_reps(self):
@@ -954,7 +974,7 @@ class MerlotModel(object):
     # ---------------------------------------------------------------------------------------------------------
     # backward of the whole model: call after mask_loss / contrastive_loss / temporal_loss (whichever are in the loss)
     # ---------------------------------------------------------------------------------------------------------
-    def backward(self, on_non_vit_grads_ready=None, vit_layer_groups=None, on_vit_group_done=None):
+    def backward(self, on_non_vit_grads_ready=None, vit_layer_groups=None, on_vit_group_done=None, d_hidden_state=None):
         """d(lang_loss + contr_loss + temp_loss)/d(params) accumulated into store.g  (model/modeling.py:713 loss,
         utils/optimization.py:176 tf.gradients).  Order: heads -> joint encoder -> language-only encoder -> (callback: every
         gradient outside vision_backbone/vision_transformer is final; data-parallel training starts their all-reduce here)
@@ -966,6 +986,10 @@ class MerlotModel(object):
         Sj, Pz, vcl, Sv, Mv, np_, ncls = D["Sj"], D["Pz"], D["vcl"], D["Sv"], D["Mv"], D["np"], D["ncls"]
         vt = "vision_backbone/vision_transformer"
         d_yj = bf.get("bwd.d_yj", (B * Sj, H), torch.bfloat16, zero=True)
+        if d_hidden_state is not None:  # gradient of an external head (e.g. downstream/vcr's classifier) w.r.t. encoder_info['hidden_state']
+            if tuple(d_hidden_state.shape) not in ((B * Sj, H), (B, Sj, H)) or d_hidden_state.dtype != torch.bfloat16:
+                raise ValueError("d_hidden_state must be bf16 [B, P+L, H]")
+            d_yj.copy_(d_hidden_state.reshape(B * Sj, H))
         d_img_trg = bf.get("bwd.d_img_trg", (N, H), torch.float32, zero=True)
         d_lang_trg = None
         if self._mask_input:
@@ -997,11 +1021,16 @@ class MerlotModel(object):
         # lang piece: embed_norm(position_embeddings) -> word / position tables
         self._embed_bwd("emb_j", "position_embeddings", self._ids_j, d_jin, (Lj, Sj, Pz), (p_emb, self._seed, _SITE_EMB_J), B, Lj)
         # viz piece: final_ln -> K7 backward
-        dxz = bf.get("bwd.dxsum_z", (B * Pz, H), torch.float32)
-        ops.layernorm_bwd(d_jin, bf.get("viz.xsum", (B * Pz, H), torch.float32), bf.get("viz.mean", (B * Pz,), torch.float32),
-                          bf.get("viz.rstd", (B * Pz,), torch.float32), st.P("vision_backbone/LayerNorm_final_ln/gamma"), dxz,
-                          st.G("vision_backbone/LayerNorm_final_ln/gamma"), st.G("vision_backbone/LayerNorm_final_ln/beta"),
-                          rows=B * Pz, remap=(Pz, Sj, 0))
+        nt = self.num_texts
+        Bi = B // nt
+        dxz = None
+        for j in range(nt):  # the nt texts of an image group all send gradient into the same viz tokens: summed through `dres`
+            dxj = bf.get(f"bwd.dxsum_z.{j & 1}", (Bi * Pz, H), torch.float32)
+            ops.layernorm_bwd(d_jin, bf.get("viz.xsum", (Bi * Pz, H), torch.float32), bf.get("viz.mean", (Bi * Pz,), torch.float32),
+                              bf.get("viz.rstd", (Bi * Pz,), torch.float32), st.P("vision_backbone/LayerNorm_final_ln/gamma"), dxj,
+                              st.G("vision_backbone/LayerNorm_final_ln/gamma"), st.G("vision_backbone/LayerNorm_final_ln/beta"),
+                              dres=dxz, rows=Bi * Pz, remap=(Pz, nt * Sj, j * Sj))
+            dxz = dxj
         d_hv = bf.get("bwd.d_hv", (Mv, H), torch.bfloat16)
         ops.viz_assemble_bwd(dxz, d_img_trg, d_hv, N, D["h1"], D["w1"], ncls, D["sp"], H)
         ops.segment_rowsum_scatter(dxz, N, vcl, self._img_idx, st.G("vision_backbone/img_idx_pe"), H)

@@ -151,6 +151,16 @@ def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_a
     return dqkv
 
 
+def attention_probs(qkv, lse, B, S, heads, valid=None, out=None):
+    """Export path: head-mean probabilities [B,S,S] fp32 of one layer (one layer of `self_attn_probs`)."""
+    a = _attn_desc(qkv, B, S, heads, valid)
+    if out is None:
+        out = torch.empty((B, S, S), dtype=torch.float32, device=qkv.device)
+    a.lse = lse.data_ptr()
+    L.check(L.lib().merlot_attention_probs(C.byref(a), C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
 def attention_colsum(qkv, lse, colsum, B, S, heads, valid=None):
     """K4: colsum[B,S] += mean_h sum_q P[b,h,q,k] (recomputed from q,k,lse)."""
     a = _attn_desc(qkv, B, S, heads, valid)

@@ -74,3 +74,68 @@ def evaluate(all_probs: Iterable[np.ndarray]) -> Dict[str, float]:
     return {"spearman": float(np.mean([spearman_acc(s) for s in stories])),
             "absolute_distance": float(np.mean([absolute_distance(s) for s in stories])),
             "pairwise": float(np.mean([pairwise_acc(s) for s in stories])), "stories": stories}
+
+
+def write_logits_h5(path: str, predictions: Iterable[Dict], include_images: bool = True) -> int:
+    """The writer loop of get_zero_shot_logits.py:105-119: one HDF5 group per story id with `permutation_identity_encode`,
+    optional uint8 `images` (255 * image), `sentences`, and `{lang_viz,viz_viz}_probs`; a story id seen twice is skipped like the
+    reference's `except ValueError: continue`.  `predictions` yields per-story dicts (what estimator.predict yields there; here
+    e.g. {'story_id': id, 'lang_viz_probs': temporal_probs(model)[i].cpu().numpy(), ...}).  Returns the number of groups written.
+    Needs h5py (not part of this image: raises ImportError with that message instead of writing another format silently)."""
+    try:
+        import h5py
+    except ImportError as e:  # pragma: no cover - depends on the environment
+        raise ImportError("write_logits_h5 needs h5py (downstream/sort_story/get_zero_shot_logits.py:105 writes HDF5); "
+                          "use write_logits_npz for an h5py-free container with the same keys") from e
+    n = 0
+    with h5py.File(path, "w") as h5:
+        for x in predictions:
+            key = str(x["story_id"])
+            if key in h5:
+                continue
+            grp = h5.create_group(key)
+            grp.create_dataset("permutation_identity_encode", data=np.asarray(x["permutation_identity_encode"]))
+            if include_images and "images" in x:
+                grp.create_dataset("images", data=(255 * np.asarray(x["images"], dtype=np.float32)).astype(np.uint8))
+            grp.create_dataset("sentences", data=np.asarray(x["sentences"]))
+            for modality_name in ("lang_viz", "viz_viz"):
+                grp.create_dataset(f"{modality_name}_probs", data=np.asarray(x[f"{modality_name}_probs"]))
+            n += 1
+    return n
+
+
+def write_logits_npz(path: str, predictions: Iterable[Dict], include_images: bool = False) -> int:
+    """Same records as write_logits_h5 in a NumPy .npz (keys `<story_id>/<dataset>`), for environments without h5py;
+    read_logits_npz gives back {story_id: {dataset: array}} -- the structure score_permutations.py walks (:77-87)."""
+    out, seen = {}, set()
+    for x in predictions:
+        key = str(x["story_id"])
+        if key in seen:
+            continue
+        seen.add(key)
+        out[f"{key}/permutation_identity_encode"] = np.asarray(x["permutation_identity_encode"])
+        if include_images and "images" in x:
+            out[f"{key}/images"] = (255 * np.asarray(x["images"], dtype=np.float32)).astype(np.uint8)
+        out[f"{key}/sentences"] = np.asarray(x["sentences"])
+        for modality_name in ("lang_viz", "viz_viz"):
+            out[f"{key}/{modality_name}_probs"] = np.asarray(x[f"{modality_name}_probs"])
+    np.savez_compressed(path, **out)
+    return len(seen)
+
+
+def read_logits_npz(path: str) -> Dict[str, Dict[str, np.ndarray]]:
+    res: Dict[str, Dict[str, np.ndarray]] = {}
+    with np.load(path) as z:
+        for k in z.files:
+            sid, name = k.split("/", 1)
+            res.setdefault(sid, {})[name] = z[k]
+    return res
+
+
+def fixed_shuffle_index(batch_size: int, num_chunks: int, seed: int = 1234) -> np.ndarray:
+    """The evaluation-time frame order of get_zero_shot_logits.py:55-56: argsort of a FIXED uniform draw per story, + 64 (the
+    'hard' index range of temporal_loss, model/modeling.py:635).  The reference draws with tf.random.stateless_uniform(seed=
+    [123, 1234]); that generator cannot be reproduced without TensorFlow, so the order differs from the reference's but is
+    equally fixed (stated in INTEGRATION.md)."""
+    rng = np.random.RandomState(seed)
+    return (np.argsort(rng.uniform(size=(batch_size, num_chunks)), 1).astype(np.int32) + 64)

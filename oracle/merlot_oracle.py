@@ -411,8 +411,9 @@ class MerlotOracle:
         self.config = copy.deepcopy(config)
         self.p = params
         cfg = self.config
-        if cfg.get("num_imgs", 1) != 1 or cfg.get("num_texts", 1) != 1:
-            raise NotImplementedError("oracle: num_imgs/num_texts > 1 (VCR path, modeling.py:111-122) not restated")
+        if cfg.get("num_imgs", 1) != 1:
+            raise NotImplementedError("oracle: num_imgs > 1 (modeling.py:111-122) not restated (no shipped config sets it)")
+        self.num_texts = cfg.get("num_texts", 1)
         if cfg.get("disable_pairwise_lang_attn", False):
             raise NotImplementedError("oracle: disable_pairwise_lang_attn (modeling.py:160-168) not restated")
         if input_ids.dim() == 2:  # :72-77
@@ -435,6 +436,9 @@ class MerlotOracle:
         self.img_trg_h = vit["cls"][:, 1]  # :99
         feats = torch.cat([vit["cls"][:, 0, None], vit["seq"]], 1)  # :101-104
         self.viz_chunk_length = vit["num_h"] * vit["num_w"] + 1
+        if self.num_texts > 1:  # VCR: every image is paired with num_texts candidate texts (:111-119): features tiled per text
+            assert shuffled_idx_img is None  # :319-320
+            feats = feats.reshape(self.B // self.num_texts, 1, self.P, H).expand(-1, self.num_texts, -1, -1)
         feats = feats.reshape(self.B, self.P, H)  # :121
         feats = feats + self.vision_pos_emb(shuffled_idx_img)  # :125
         feats = layer_norm(feats, params, "vision_backbone/LayerNorm_final_ln")  # :126
@@ -625,6 +629,13 @@ class MerlotOracle:
         if cfg.get("image_shuffle_prob", 0) > 0:  # :664-665
             info["loss"] = info["loss"] + info["viz_viz_loss"]
         return info["loss"] * cfg.get("temporal_coef", 1.0), info
+
+
+def vcr_cls_head_val(model: "MerlotOracle", p: Params, mode: str = "answer") -> torch.Tensor:
+    """downstream/vcr/modeling.py:57-77: first language token -> dense(H/2, gelu) -> dense(1) -> [img_batch, 4]."""
+    first = model.encoder_hidden_states["lang"][:, 0, :]
+    h = dense(first, p, f"{mode}_cls/classifier_mlp0", gelu)
+    return dense(h, p, f"{mode}_cls/classifier_mlp1").reshape(-1, 4)
 
 
 def contrastive_loss_replicas(models, rank: int):

@@ -206,3 +206,66 @@ def test_partial_stack_backward_equals_full(tiny_cfg):
         assert seen == ([] if groups is None else [0, 1, 2])
     assert rel(gs[1], gs[0]) < 1e-3
     store.g.zero_()
+
+
+def test_exported_attention_probabilities(tiny_cfg):
+    """encoder_info / lang_transformer_info['self_attn_probs'] (model_fn PREDICT outputs, model/modeling.py:762-770): head-mean
+    probabilities [B, layers, S, S] against the oracle's transformer(return_attn_probs=True); rows sum to one."""
+    from merlot_b200.modeling import MerlotModel
+    cfg = tiny_cfg
+    image, ids, shuf, vid = synth(cfg, 2, 4, 16, 64, 96, 0)
+    params, store, _ = build(cfg)
+    draws = O.make_mask_draws(4, 32, 6, cfg["vocab_size"], seed=5)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, export_attention_probs=True)
+    gm = {"masked_ids": m.lang_mask_info["masked_ids"].cpu().reshape(4, 32), "masked_idx": m.lang_mask_info["masked_idx"].cpu()}
+    om = O.MerlotOracle(cfg, params, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)
+    pj, pl = m.encoder_info["self_attn_probs"], m.lang_transformer_info["self_attn_probs"]
+    assert tuple(pj.shape) == tuple(om.encoder_info["self_attn_probs"].shape)
+    assert tuple(pl.shape) == tuple(om.lang_transformer_info["self_attn_probs"].shape)
+    assert rel(pl, om.lang_transformer_info["self_attn_probs"]) < 5e-3
+    assert rel(pj, om.encoder_info["self_attn_probs"]) < 1e-2  # second layer sees bf16 activations of the first
+    assert float((pj.sum(-1) - 1).abs().max()) < 2e-3
+
+
+def test_vcr_num_texts_tiling_and_cls_head(tiny_cfg):
+    """merlot_vcr.yaml's num_texts: 4 (model/modeling.py:111-119): every image's tokens are tiled to its four candidate texts;
+    plus downstream/vcr's validation head and loss.  Forward against the oracle; backward of an external head's gradient
+    (d_hidden_state) against autograd: the four texts' gradients meet in the shared image tokens."""
+    from merlot_b200 import vcr
+    from merlot_b200.modeling import MerlotModel
+    cfg = dict(tiny_cfg, num_texts=4, num_chunks_in_group=1)
+    g = torch.Generator().manual_seed(3)
+    nimg, L = 3, 16
+    image = torch.rand(nimg, 64, 96, 3, generator=g).bfloat16().float()
+    ids = torch.randint(100, cfg["vocab_size"], (nimg * 4, L), generator=g)
+    ids[:, 0] = O.START
+    ids[:, 12:] = 0
+    ids = ids.int()
+    params, store, _ = build(cfg)
+    head = vcr.init_head(cfg["hidden_size"], "answer", seed=1, device=DEV)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), params=store, save_for_backward=True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    om = O.MerlotOracle(cfg, leaf, image, ids)
+    assert (m.B, m.img_batch_size, m.P) == (12, 3, om.P)
+    for name in ("viz", "lang"):
+        assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 1e-2
+    hp = {k: v.float().cpu() for k, v in head.items()}
+    hp = {k: (v.bfloat16().float() if k.endswith("kernel") else v) for k, v in hp.items()}
+    logits = vcr.cls_head_val(m, head, "answer")
+    ref = O.vcr_cls_head_val(om, hp, "answer")
+    assert tuple(logits.shape) == (3, 4) and rel(logits, ref) < 1e-2
+    target = torch.tensor([1, 3, 0])
+    loss, acc = vcr.cls_loss(logits, target.to(DEV))
+    ref_loss = torch.nn.functional.cross_entropy(ref, target, reduction="sum") / 3  # downstream/vcr/modeling.py:141-142
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * abs(float(ref_loss))
+    # an external head's gradient through the tiled model: d(sum of first-language-token features . w)
+    Sj, H = m._dims["Sj"], cfg["hidden_size"]
+    w = (torch.randn(12, Sj, H, generator=g) * 0.05).bfloat16()
+    store.g.zero_()
+    m.backward(d_hidden_state=w.to(DEV))
+    (om.encoder_info["hidden_state"] * w.float()).sum().backward()
+    grads = store.to_tf_dict("g")
+    worst = {k: rel(grads[k], v.grad) for k, v in leaf.items() if v.grad is not None and float(v.grad.norm()) > 1e-7}
+    assert len(worst) > 40 and max(worst.values()) < 4e-2, sorted(worst.items(), key=lambda kv: -kv[1])[:4]
+    store.g.zero_()

@@ -260,3 +260,31 @@ def test_multi_replica_contrastive_restatement_reduces_to_single_replica():
     assert torch.allclose(O.raw_cross_entropy_with_logits(logits, torch.arange(n) + n).mean() * 0.125 +
                           O.raw_cross_entropy_with_logits(vx @ torch.cat([oms[0]._ctr_feats[0], lx], 0).t() / 0.05, torch.arange(n) + n).mean() * 0.125,
                           two1)
+
+
+def test_sort_story_logit_container_round_trip(tmp_path):
+    """write_logits_npz / read_logits_npz carry the records of get_zero_shot_logits.py:105-119 (h5py is not in this image; the
+    HDF5 writer raises ImportError instead of silently writing something else) and feed the scorer unchanged."""
+    import numpy as np
+    import pytest
+    from merlot_b200 import sort_story as ss
+    rng = np.random.RandomState(0)
+    preds = []
+    for sid in (7, 9, 7):  # a duplicate story id is skipped, like the reference's `except ValueError: continue`
+        p = rng.dirichlet(np.ones(3), size=(5, 5))
+        preds.append({"story_id": sid, "permutation_identity_encode": rng.permutation(5), "sentences": rng.randint(0, 100, (5, 32)),
+                      "lang_viz_probs": p, "viz_viz_probs": p[::-1].copy(), "images": rng.rand(5, 4, 4, 3)})
+    path = str(tmp_path / "logits_val.npz")
+    assert ss.write_logits_npz(path, preds, include_images=True) == 2
+    back = ss.read_logits_npz(path)
+    assert sorted(back) == ["7", "9"] and back["7"]["images"].dtype == np.uint8
+    assert np.array_equal(back["9"]["lang_viz_probs"], preds[1]["lang_viz_probs"])
+    perms, scores = ss.permutation_scores(back["7"]["lang_viz_probs"])
+    assert perms.shape == (120, 5) and np.isfinite(scores).all()
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            ss.write_logits_h5(str(tmp_path / "x.h5"), preds)
+    idx = ss.fixed_shuffle_index(3, 5)
+    assert idx.shape == (3, 5) and all(sorted(r - 64) == list(range(5)) for r in idx) and np.array_equal(idx, ss.fixed_shuffle_index(3, 5))
