@@ -289,6 +289,11 @@ typedef struct merlot_mask {
   float w_delta, w_non, logw_top, logw_non, w_max;
 } merlot_mask_t;
 int merlot_mask_inputs(const merlot_mask_t* m, void* stream);
+/* The five random tensors of mask_inputs drawn on device (Philox keyed by seed): gumbel f32 [n_tok] = -log(-log U),
+ * span_lower/upper int32 [n_span] ~ categorical(p_len0, p_len1, 1-p_len0-p_len1), option int32 [n_tok] ~ (0.1, 0.8, 0.1),
+ * rand_ids int32 [n_tok] uniform in [100, vocab)  (model/modeling.py:445-481, utils/model_utils.py:640-649). */
+int merlot_mask_draws(float* gumbel, int* span_lower, int* span_upper, int* option, int* rand_ids, long long n_tok, long long n_span,
+                      int vocab, float p_len0, float p_len1, uint64_t seed, void* stream);
 int merlot_ids_valid(const int* ids, void* valid_u8, long long n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

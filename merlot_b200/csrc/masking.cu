@@ -114,6 +114,51 @@ __global__ void ids_valid_kernel(const int* __restrict__ ids, uint8_t* __restric
   if (i < n) valid[i] = ids[i] != 0;
 }
 
+// The five tf.random draws of mask_inputs (model/modeling.py:445-481, utils/model_utils.py:640-649) on device: counter-based
+// Philox keyed by (seed, tensor id), so a step is reproducible from its seed and no host RNG / pageable host->device copy sits
+// in the step (the reference draws them inside the TF graph as well).  Same distributions as the reference; the bit streams of
+// tf.random cannot be reproduced.
+//   gumbel  [B*L]  = -log(-log(U)), U uniform in [1e-9, 1 - 1e-7]      span_lower/upper [B*k] ~ categorical(span_probs)
+//   option  [B*L]  ~ categorical(0.1 keep, 0.8 [MASK], 0.1 random)     rand_ids [B*L] uniform in [100, vocab)
+__global__ void mask_draws_kernel(float* __restrict__ gumbel, int* __restrict__ span_lower, int* __restrict__ span_upper,
+                                  int* __restrict__ option, int* __restrict__ rand_ids, long long n_tok, long long n_span, int vocab,
+                                  float p0, float p1, uint64_t seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  auto u01 = [](uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); };  // (0,1), 24 bits
+  if (i < n_tok) {
+    const uint4 r = philox4x32_7(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0x6d61736bu, 1u), key);
+    const float u = fminf(fmaxf(u01(r.x), 1e-9f), 1.0f - 1e-7f);
+    gumbel[i] = -logf(-logf(u));
+    const float o = u01(r.y);
+    option[i] = o < 0.1f ? 0 : (o < 0.9f ? 1 : 2);
+    rand_ids[i] = 100 + (int)(((uint64_t)r.z * (uint64_t)(vocab - 100)) >> 32);
+  }
+  if (i < n_span) {
+    const uint4 r = philox4x32_7(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0x7370616eu, 2u), key);
+    const float a = u01(r.x), b = u01(r.y);
+    span_lower[i] = a < p0 ? 0 : (a < p0 + p1 ? 1 : 2);
+    span_upper[i] = b < p0 ? 0 : (b < p0 + p1 ? 1 : 2);
+  }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int merlot_mask_draws(float* gumbel, int* span_lower, int* span_upper, int* option, int* rand_ids, long long n_tok,
+                                 long long n_span, int vocab, float p_len0, float p_len1, uint64_t seed, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MB_REQUIRE(gumbel && span_lower && span_upper && option && rand_ids, MERLOT_EINVAL, "mask_draws: null output");
+  MB_REQUIRE(n_tok > 0 && n_span >= 0 && vocab > 100, MERLOT_ESHAPE, "mask_draws: bad sizes (vocab must exceed 100)");
+  const long long n = n_tok > n_span ? n_tok : n_span;
+  mask_draws_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(gumbel, span_lower, span_upper, option, rand_ids, n_tok, n_span, vocab,
+                                                                     p_len0, p_len1, seed);
+  MB_CHECK_LAUNCH();
+  return MERLOT_OK;
+}
+
+namespace mb {
 }  // namespace mb
 
 using namespace mb;

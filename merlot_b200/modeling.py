@@ -628,9 +628,12 @@ class MerlotModel(object):
                       float(w.max()))
         else:
             consts = (0.0, 1.0, 0.0, 0.0, 1.0)
-        if draws is None:
-            draws = self.make_mask_draws(B, Lj, num_to_mask, self.vocab_size, span_probs, dev, seed=self._seed)
-        draws = {k: v.to(dev).contiguous() for k, v in draws.items()}
+        if draws is None:  # drawn on device (Philox keyed by the step seed): nothing in the step waits for the host
+            key = ("mask.draws", B, Lj, num_to_mask)
+            draws = ops.mask_draws(B, Lj, num_to_mask, self.vocab_size, span_probs, 1234567 + self._seed, dev, out=bf.d.get(key))
+            bf.d[key] = draws
+        else:  # injected draws (tests, reproducing a reference run's tf.random tensors)
+            draws = {k: v.to(dev).contiguous() for k, v in draws.items()}
         masked_ids = bf.get("mask.ids", (B, Lj), torch.int32)
         masked_idx = bf.get("mask.idx", (B, num_to_mask), torch.int32)
         summ = self.lang_transformer_info["attention_summs"] if use_attn else None

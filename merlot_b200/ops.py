@@ -426,6 +426,21 @@ def axpby(x, y, a=1.0, b=1.0):
                                      C.c_float(b), _stream()))
 
 
+def mask_draws(B, Lseq, num_to_mask, vocab_size, span_probs, seed, device, out=None):
+    """The tf.random draws of mask_inputs on device (no host RNG, no host->device copy); returns the dict mask_inputs takes."""
+    if out is None:
+        out = {"gumbel": torch.empty((B, Lseq), dtype=torch.float32, device=device),
+               "span_lower": torch.empty((B, max(num_to_mask, 1)), dtype=torch.int32, device=device),
+               "span_upper": torch.empty((B, max(num_to_mask, 1)), dtype=torch.int32, device=device),
+               "option": torch.empty((B * Lseq,), dtype=torch.int32, device=device),
+               "rand_ids": torch.empty((B * Lseq,), dtype=torch.int32, device=device)}
+    L.check(L.lib().merlot_mask_draws(C.c_void_p(out["gumbel"].data_ptr()), C.c_void_p(out["span_lower"].data_ptr()),
+                                      C.c_void_p(out["span_upper"].data_ptr()), C.c_void_p(out["option"].data_ptr()),
+                                      C.c_void_p(out["rand_ids"].data_ptr()), C.c_longlong(B * Lseq), C.c_longlong(B * num_to_mask),
+                                      int(vocab_size), C.c_float(span_probs[0]), C.c_float(span_probs[1]), C.c_uint64(seed), _stream()))
+    return out
+
+
 def mask_inputs(ids, attn_summ, draws, masked_ids, masked_idx, valid_out, num_topk, num_to_mask, do_spanbert, mask_token, consts):
     m = L.MaskDesc()
     B, Lseq = ids.shape

@@ -320,3 +320,38 @@ def test_clip_by_global_norm(ops):
         assert abs(float(norm) - ref_norm) < 1e-5 * ref_norm
         ref = x * (clip / max(ref_norm, clip))
         assert rel(gd, ref) < 1e-6
+
+
+def test_device_mask_draws_distributions_and_bit_exact_masking(ops):
+    """merlot_mask_draws: the five tf.random tensors of mask_inputs drawn on device -- right distributions, reproducible from
+    the seed -- and K12 fed with them is bit-exact against the oracle fed the very same tensors."""
+    from merlot_b200 import ops as o
+    B, L, k, V = 64, 128, 25, 50370
+    d = o.mask_draws(B, L, k, V, [0.625, 0.25, 0.125], seed=11, device=DEV)
+    d2 = o.mask_draws(B, L, k, V, [0.625, 0.25, 0.125], seed=11, device=DEV)
+    d3 = o.mask_draws(B, L, k, V, [0.625, 0.25, 0.125], seed=12, device=DEV)
+    assert all(torch.equal(d[x], d2[x]) for x in d) and not torch.equal(d["gumbel"], d3["gumbel"])
+    g = d["gumbel"].double().cpu()
+    assert abs(float(g.mean()) - 0.5772) < 0.03 and abs(float(g.var()) - 1.6449) < 0.1          # Gumbel(0,1): mean gamma, var pi^2/6
+    opt = torch.bincount(d["option"].cpu(), minlength=3).double() / (B * L)
+    assert (opt - torch.tensor([0.1, 0.8, 0.1])).abs().max() < 0.02
+    for name in ("span_lower", "span_upper"):
+        f = torch.bincount(d[name].reshape(-1).cpu(), minlength=3).double() / (B * k)
+        assert (f - torch.tensor([0.625, 0.25, 0.125])).abs().max() < 0.04
+    r = d["rand_ids"].cpu()
+    assert int(r.min()) >= 100 and int(r.max()) < V and abs(float(r.double().mean()) - (100 + V) / 2) < 300
+    gen = torch.Generator().manual_seed(0)
+    ids = torch.randint(100, V, (B, L), generator=gen, dtype=torch.int32)
+    ids[:, 0] = 2
+    ids[:, 100:] = 0
+    summ = torch.rand(B, L, generator=gen)
+    cfg = dict(masking_use_topk_from_attn_perc=0.2, masking_choose_topk_prob=0.5, masking_rate=0.2, masking_do_spanbert=True, masking_use_attn=True)
+    ref = O.mask_inputs(ids, summ, cfg, {x: v.cpu() for x, v in d.items()})
+    import numpy as np
+    nontop, top = 0.01, 0.01 * 0.5 * 0.8 / (0.2 * 0.5)
+    w = torch.tensor([1.0, 0.0]) * np.float32(top - nontop) + np.float32(nontop)
+    consts = (float(np.float32(top - nontop)), float(np.float32(nontop)), float(torch.log(w)[0]), float(torch.log(w)[1]), float(w.max()))
+    mi = torch.empty(B, L, dtype=torch.int32, device=DEV)
+    mx = torch.empty(B, k, dtype=torch.int32, device=DEV)
+    o.mask_inputs(ids.to(DEV), summ.to(DEV), d, mi, mx, None, 25, k, True, 1, consts)
+    assert torch.equal(mi.cpu(), ref["masked_ids"]) and torch.equal(mx.cpu(), ref["masked_idx"])
