@@ -10,7 +10,38 @@
 // red.adds fp32 into the flat gradient arena (so the shared `encoder` weights accumulate both of their passes).
 #include "host_common.h"
 
+#include <map>
+#include <mutex>
+
 namespace mb {
+
+// Weight-gradient GEMMs run on a companion stream of the stream the backward pass is enqueued on: a persistent K1 launch
+// leaves the SMs of its last partial wave idle (1.4-5.4 waves per GEMM at these shapes), and wgrad(W) and dgrad(x) of a layer
+// are independent, so the other stream's CTAs fill those tails.  Events order each wgrad behind the kernel that produces its
+// dy and hold back the kernel that overwrites that dy until the wgrad has read it.
+struct WgradLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready[4] = {nullptr, nullptr, nullptr, nullptr};  // recorded on the main stream: dy of wgrad i is final
+  cudaEvent_t done[4] = {nullptr, nullptr, nullptr, nullptr};   // recorded on the lane: wgrad i has read its operands
+};
+static WgradLane* wgrad_lane(cudaStream_t main) {
+  static std::map<cudaStream_t, WgradLane> lanes;
+  static std::mutex mu;
+  static const bool off = [] { const char* e = getenv("MERLOT_WGRAD_STREAM"); return e && e[0] == '0'; }();
+  if (off) return nullptr;
+  const char* e = getenv("MERLOT_NO_SIDE_STREAM");  // single-stream diagnostics (bench.py's per-launch event timing)
+  if (e && e[0] == '1') return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  WgradLane& w = lanes[main];
+  if (w.stream == nullptr) {
+    if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) { w.stream = nullptr; return nullptr; }
+    for (int i = 0; i < 4; ++i) {
+      cudaEventCreateWithFlags(&w.ready[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&w.done[i], cudaEventDisableTiming);
+    }
+  }
+  return &w;
+}
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -210,6 +241,30 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
   if (merlot_attention_bwd_dq_parts(s->S) == 0)  // atomic mode: the single slice must start at zero (K3 hands it back zeroed)
     MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)M * H * 4, st));
 
+  WgradLane* lane = wgrad_lane(st);
+  cudaStream_t wst = lane ? lane->stream : st;
+  bool pending[4] = {false, false, false, false};  // wgrad i of the previous use still has to be waited for by its overwriter
+  // wgrad i: ordered behind everything enqueued on the main stream so far; `done[i]` marks the end of its reads
+  auto wgrad_on_lane = [&](int i, const void* x, int K, const void* dy, int N, float* dW) -> int {
+    if (lane) {
+      MB_CHECK_CUDA(cudaEventRecord(lane->ready[i], st));
+      MB_CHECK_CUDA(cudaStreamWaitEvent(wst, lane->ready[i], 0));
+    }
+    int rc = linear_wgrad(x, K, dy, N, dW, M, wst);
+    if (rc) return rc;
+    if (lane) {
+      MB_CHECK_CUDA(cudaEventRecord(lane->done[i], wst));
+      pending[i] = true;
+    }
+    return MERLOT_OK;
+  };
+  auto wait_wgrad = [&](int i) -> int {  // the next main-stream kernel overwrites what wgrad i reads
+    if (lane && pending[i]) {
+      MB_CHECK_CUDA(cudaStreamWaitEvent(st, lane->done[i], 0));
+      pending[i] = false;
+    }
+    return MERLOT_OK;
+  };
   const bool drop = s->hidden_dropout_p > 0.f;
   // ln_bwd(dy, x, stats, gamma, dres) -> dx [+ dropout-masked copy + bias gradient of the linear layer that fed this
   // residual add]; `next_bias`/`next_site` describe that layer (nullptr: nobody consumes a masked copy)
@@ -239,7 +294,8 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
     const void* h_in = (l == 0) ? s->h_in : (const void*)carve(s, arena + per * (l - 1)).hout;
     // ---- FFN2: hout = hmid + drop(act W2 + b2);  d = dropout_bwd(dh) and db2 were produced by the LN backward above ----
     const void* d = drop ? (const void*)dmask : (const void*)dh;
-    RC(linear_wgrad(A.act, I, d, H, P.g_w_2, M, st));
+    RC(wgrad_on_lane(0, A.act, I, d, H, P.g_w_2));
+    RC(wait_wgrad(1));  // dpre is about to be rewritten: the previous layer's W1 wgrad has to be through with it
     {
       merlot_gemm_t e = gemm_base(0, 0, 0);
       e.flags = MERLOT_GEMM_MUL_AUX; e.aux = A.pre; e.ld_aux = I;  // A.pre = gelu'(pre), saved by the forward epilogue
@@ -247,17 +303,19 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
     }
     // ---- FFN1 ----
     RC(merlot_bias_grad(dpre, 0, I, M, I, P.g_b_1, 0.f, 0, 0, st));
-    RC(linear_wgrad(A.x2, H, dpre, I, P.g_w_1, M, st));
+    RC(wgrad_on_lane(1, A.x2, H, dpre, I, P.g_w_1));
     RC(linear_dgrad(dpre, I, P.w_1, H, dtmp, M, gemm_base(0, 0, 0), st));
     // ---- LN2: d_hmid = dh + LN'(dx2); also emits dropout_bwd(d_hmid) and db_o for the out-projection ----
+    RC(wait_wgrad(0));  // it rewrites dmask / the other stream-gradient buffer
     RC(ln_bwd_f(dtmp, A.hmid, A.mean2, A.rstd2, P.ln2_gamma, dh, dh_other, P.g_ln2_gamma, P.g_ln2_beta, P.g_b_o,
                 s->dropout_site_base + 2 * l));
     { char* t = dh; dh = dh_other; dh_other = t; }
     // ---- attention output projection: hmid = h + drop(ctx Wo + bo) ----
     d = drop ? (const void*)dmask : (const void*)dh;
-    RC(linear_wgrad(A.ctx, H, d, H, P.g_w_o, M, st));
+    RC(wgrad_on_lane(2, A.ctx, H, d, H, P.g_w_o));
     RC(linear_dgrad(d, H, P.w_o, H, dtmp, M, gemm_base(0, 0, 0), st));  // d_ctx
     // ---- attention ----
+    RC(wait_wgrad(3));  // dqkv is about to be rewritten: the previous layer's QKV wgrad has to be through with it
     {
       merlot_attn_t a;
       memset(&a, 0, sizeof(a));
@@ -267,14 +325,16 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
       RC(merlot_attention_bwd(&a, st));
     }
     // ---- QKV projection ----
-    RC(linear_wgrad(A.x1, H, dqkv, 3 * H, P.g_w_qkv, M, st));
+    RC(wgrad_on_lane(3, A.x1, H, dqkv, 3 * H, P.g_w_qkv));
     RC(linear_dgrad(dqkv, 3 * H, P.w_qkv, H, dtmp, M, gemm_base(0, 0, 0), st));
     // ---- LN1: d_h_in = d_hmid + LN'(dx1); feeds the previous layer's FFN2 ----
+    RC(wait_wgrad(2));  // it rewrites dmask / the other stream-gradient buffer
     void* dst = (l == 0 && s->dh_in) ? s->dh_in : (void*)dh_other;
     float* nb = (l > 0) ? s->layer_params[l - 1].g_b_2 : nullptr;
     RC(ln_bwd_f(dtmp, h_in, A.mean1, A.rstd1, P.ln1_gamma, dh, dst, P.g_ln1_gamma, P.g_ln1_beta, nb,
                 l > 0 ? s->dropout_site_base + 2 * (l - 1) + 1 : 0));
     { char* t = dh; dh = dh_other; dh_other = t; }
   }
+  for (int i = 0; i < 4; ++i) RC(wait_wgrad(i));  // join: every parameter gradient of these layers is final on the caller's stream
   return MERLOT_OK;
 }
