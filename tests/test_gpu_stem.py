@@ -290,7 +290,7 @@ def test_stem_backward_in_situ(tiny_cfg):
 def test_training_step_through_the_stem(tiny_cfg, monkeypatch):
     """Whole pretraining step with the hybrid stem; the oracle's lite_resnet50 is replaced by a LEAF holding the GPU's stem
     output, so the two graphs share their rounding points at the stem boundary: the three losses, every non-stem gradient and the
-    gradient handed to the stem are compared at the bars of the patch-embed model test (1e-3 losses, 4e-2 gradients)."""
+    gradient handed to the stem are compared at bf16 noise-floor bars (1e-3 losses; gradients 6e-2 worst tensor, 2.5e-2 median, 4e-2 at the stem boundary)."""
     cfg, m, params, store, (image, ids, shuf, vid) = _stem_model(tiny_cfg, 128, 192)
     N = image.shape[0]
     rc = m._stem_tape[-1][1]["y"]
@@ -322,7 +322,11 @@ def test_training_step_through_the_stem(tiny_cfg, monkeypatch):
     vals = sorted(worst.values())
     print(f"stem boundary: d(stem out) rel {e_rc:.3e}; non-stem worst {max(worst.values()):.3e} median {vals[len(vals) // 2]:.3e}; "
           f"stem grad norm sum {stem_norm:.3e}; worst tensors {top}")
-    assert max(worst.values()) < 4e-2, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    # bf16 noise floor of this graph: the worst single tensor of ~115 sits at 3.7-3.9e-2 run to run (the red.add order of the
+    # split-K wgrads is not fixed), so the bar on the worst tensor is 6e-2 and the tighter bar goes on the median; a wrong
+    # backward shows up at O(0.1-1) (the broken stem of round 1 measured 0.39 worst / 0.26 median).
+    assert max(worst.values()) < 6e-2, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    assert vals[len(vals) // 2] < 2.5e-2, vals[len(vals) // 2]
     assert e_rc < 4e-2
     assert stem_norm > 0 and all(torch.isfinite(grads[k]).all() for k in grads)
     store.g.zero_()
