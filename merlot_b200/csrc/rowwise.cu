@@ -211,6 +211,28 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDY* __restrict__ dy,
 // x and dy stay packed (bf16x2) in registers between the two sweeps so 2 blocks of 8 warps fit per SM.
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int LNF_WARPS = 12;  // one block of 12 warps per SM: the column partials meet in smem, one red.add set per block
+constexpr int LNF_STAGES = 3;  // rows in flight per warp
+// Rows reach the warp through a private ring of LNF_STAGES row slots filled by 1-D bulk copies (cp.async.bulk, completion on
+// an mbarrier of the warp): the loads of the next two rows are in the air while a row is reduced, so the per-row chain
+// load -> reduce -> store no longer pays the memory latency once per row (it ran at ~2.5 TB/s with register loads).
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__host__ __device__ constexpr size_t lnf_smem_bytes(int H) {  // ring [warp][stage][x | dy | dres][H] bf16 (the fp32 column partials reuse it) + barriers
+  return (size_t)LNF_WARPS * LNF_STAGES * 3 * H * 2 + (size_t)LNF_WARPS * LNF_STAGES * 8;
+}
+// one lane: fetch row r (the warp's k-th) into slot k % LNF_STAGES of the warp's ring
+__device__ __forceinline__ void lnf_issue(uint8_t* ring, uint64_t* bar, int k, long long r, const bf16* x, const bf16* dy, const bf16* dres, int H) {
+  const int s = k % LNF_STAGES;
+  const uint32_t row_bytes = (uint32_t)H * 2u;
+  uint8_t* slot = ring + (size_t)s * 3 * row_bytes;
+  mbar_arrive_expect_tx(&bar[s], (dres != nullptr ? 3u : 2u) * row_bytes);
+  bulk_load_row(slot, x + (size_t)r * H, row_bytes, &bar[s]);
+  bulk_load_row(slot + row_bytes, dy + (size_t)r * H, row_bytes, &bar[s]);
+  if (dres != nullptr) bulk_load_row(slot + 2 * row_bytes, dres + (size_t)r * H, row_bytes, &bar[s]);
+}
 template <int NCH>  // 16-byte chunks per lane: NCH = ceil(H / 256), H % 8 == 0 (H = 768 -> NCH = 3)
 __global__ void __launch_bounds__(32 * LNF_WARPS, 1)
 ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
@@ -218,27 +240,52 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
                     bf16* __restrict__ dx, bf16* __restrict__ dmask, float* __restrict__ out_g, float* __restrict__ out_b,
                     float* __restrict__ out_bias, long long rows, int H, int want_bias,
                     uint32_t drop_thresh16, float drop_scale, uint64_t seed, uint32_t site) {
-  extern __shared__ float sred[];  // [LNF_WARPS][3][H]: every warp's column partials (dgamma | dbeta | bias)
+  extern __shared__ __align__(16) uint8_t lnf_smem[];
+  float* sred = reinterpret_cast<float*>(lnf_smem);  // after the row loop: [LNF_WARPS][3][H] column partials (dgamma | dbeta | bias)
   pdl_launch_dependents();
   const int nchunk = H >> 3;
   const float invH = 1.0f / (float)H;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // warp index through a shuffle + elect.sync: the bulk copies take uniform-register operands (see gemm_kernel.cuh)
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), nwarp = blockDim.x >> 5;
+  const bool leader = elect_one();
+  const uint32_t row_bytes = (uint32_t)H * 2u;
+  uint8_t* ring = lnf_smem + (size_t)warp * LNF_STAGES * 3 * row_bytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(lnf_smem + (size_t)LNF_WARPS * LNF_STAGES * 3 * row_bytes) + warp * LNF_STAGES;
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < LNF_STAGES; ++s) mbar_init(&bar[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  const long long row0 = (long long)blockIdx.x * nwarp + warp, row_step = (long long)gridDim.x * nwarp;
+  const int n_my = row0 < rows ? (int)((rows - row0 + row_step - 1) / row_step) : 0;
   pdl_wait();
+  if (leader) {
+    for (int k = 0; k < LNF_STAGES && k < n_my; ++k) lnf_issue(ring, bar, k, row0 + (long long)k * row_step, x, dy, dres, H);
+  }
   float dg[NCH][8], db[NCH][8], bs[NCH][8];
 #pragma unroll
   for (int j = 0; j < NCH; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[j][i] = 0.f; db[j][i] = 0.f; bs[j][i] = 0.f; }
-  for (long long row = (long long)blockIdx.x * nwarp + warp; row < rows; row += (long long)gridDim.x * nwarp) {
-    const float mu = mean[row], rs = rstd[row];
+  float mu_n = 0.f, rs_n = 0.f;
+  if (n_my > 0) { mu_n = mean[row0]; rs_n = rstd[row0]; }
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int k = 0; k < n_my; ++k) {
+    const long long row = row0 + (long long)k * row_step;
+    const float mu = mu_n, rs = rs_n;
+    if (k + 1 < n_my) { mu_n = mean[row + row_step]; rs_n = rstd[row + row_step]; }
+    const uint8_t* slot = ring + (size_t)stage * 3 * row_bytes;
+    mbar_wait(&bar[stage], phase);
     uint4 xp[NCH], dp[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int c = (lane + 32 * j) * 8;
       if (lane + 32 * j < nchunk) {
-        xp[j] = *reinterpret_cast<const uint4*>(x + (size_t)row * H + c);
-        dp[j] = *reinterpret_cast<const uint4*>(dy + (size_t)row * H + c);
+        xp[j] = *reinterpret_cast<const uint4*>(slot + (size_t)c * 2);
+        dp[j] = *reinterpret_cast<const uint4*>(slot + row_bytes + (size_t)c * 2);
       }
     }
 #pragma unroll
@@ -278,7 +325,7 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
       }
       if (dres != nullptr) {
         float r[8];
-        Vec8<bf16>::load(dres + (size_t)row * H + c, r);
+        Vec8<bf16>::load(reinterpret_cast<const bf16*>(slot + 2 * row_bytes) + c, r);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += r[i];
       }
@@ -305,7 +352,14 @@ ln_bwd_fused_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, con
         for (int i = 0; i < 8; ++i) bs[j][i] += q[i];
       }
     }
+    __syncwarp();  // every lane is done reading the slot: refill it with the row LNF_STAGES ahead
+    if (k + LNF_STAGES < n_my && leader) {
+      fence_proxy_async_smem();
+      lnf_issue(ring, bar, k + LNF_STAGES, row + (long long)LNF_STAGES * row_step, x, dy, dres, H);
+    }
+    if (++stage == LNF_STAGES) { stage = 0; phase ^= 1u; }
   }
+  __syncthreads();  // all rings drained (every issued row was waited for): the partials below reuse the ring's bytes
   // warp partials -> smem (plain stores, each warp its own [3][H] slab), summed over the warps by the whole block, then ONE
   // red.global.add per column and block (the same-address reductions of many small blocks used to be the kernel's fixed cost)
   float* mine = sred + (size_t)warp * 3 * H;
@@ -651,13 +705,16 @@ extern "C" int merlot_layernorm_bwd_fused(const void* dy, const void* x, const f
   long long want = ceil_div_ll(rows, LNF_WARPS);
   const int sms = num_sms();
   const int grid = (int)(want < sms ? want : sms);
-  const size_t smem = (size_t)LNF_WARPS * 3 * H * sizeof(float);
+  const size_t smem = lnf_smem_bytes(H);
+  MB_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dres) |
+               reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dmask)) & 15) == 0, MERLOT_EINVAL,
+             "layernorm_bwd_fused: dy, x, dres, dx, dmask must be 16-byte aligned");
   (void)workspace;
 #define LNF(N_)                                                                                                          \
   do {                                                                                                                   \
     static bool attr_set = false;                                                                                        \
     if (!attr_set) {                                                                                                     \
-      MB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_fused_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, LNF_WARPS * 3 * 1024 * 4)); \
+      MB_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_fused_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lnf_smem_bytes(1024))); \
       attr_set = true;                                                                                                   \
     }                                                                                                                    \
     MB_CHECK_CUDA(launch_pdl(ln_bwd_fused_kernel<N_>, dim3(grid), dim3(32 * LNF_WARPS), smem, st, (const bf16*)dy, (const bf16*)x, mean, \

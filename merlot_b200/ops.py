@@ -228,6 +228,27 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dres=None, rows=N
     return dx
 
 
+def layernorm_bwd_fused(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dres=None, dmask=None, dbias=None, dropout=(0.0, 0, 0)):
+    """The transformer stacks' LayerNorm backward (bf16, dense rows): dx = LN'(dy) + dres, dmask = dropout_bwd(dx),
+    dbias += colsum(dmask or dx), dgamma / dbeta accumulated."""
+    _require_cuda(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dres, dmask, dbias)
+    H = gamma.numel()
+    p, seed, site = dropout
+    L.check(L.lib().merlot_layernorm_bwd_fused(
+        C.c_void_p(dy.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(mean.data_ptr()), C.c_void_p(rstd.data_ptr()),
+        C.c_void_p(gamma.data_ptr()), C.c_void_p(_ptr(dres)), C.c_void_p(dx.data_ptr()), C.c_void_p(_ptr(dmask)),
+        C.c_void_p(dgamma.data_ptr()), C.c_void_p(dbeta.data_ptr()), C.c_void_p(_ptr(dbias)), C.c_void_p(None),
+        C.c_longlong(x.numel() // H), H, C.c_float(p), C.c_uint64(seed), C.c_uint32(site), _stream()))
+    return dx
+
+
+def dropout_apply(x, y, p, seed, site):
+    rows, N = x.numel() // x.shape[-1], x.shape[-1]
+    L.check(L.lib().merlot_dropout_apply(C.c_void_p(x.data_ptr()), x.stride(-2), C.c_void_p(y.data_ptr()), y.stride(-2),
+                                         C.c_longlong(rows), N, C.c_float(p), C.c_uint64(seed), C.c_uint32(site), _stream()))
+    return y
+
+
 def bias_grad(dy, out, rows=None, N=None):
     N = out.numel() if N is None else N
     rows = dy.numel() // dy.stride(-2) if rows is None else rows

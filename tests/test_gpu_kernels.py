@@ -216,6 +216,43 @@ def test_layernorm_fwd_bwd(ops, rows, H):
     assert rel(dg, gr.grad) < 2e-3 and rel(db, br.grad) < 2e-3
 
 
+@pytest.mark.parametrize("rows,H,with_dres,p", [(1, 768, True, 0.1), (13, 64, False, 0.0), (1777, 768, True, 0.1), (8512, 768, True, 0.1),
+                                                  (8512, 768, False, 0.0), (5000, 1024, True, 0.1), (20000, 256, True, 0.0), (3, 512, True, 0.1)])
+def test_layernorm_bwd_fused(ops, rows, H, with_dres, p):
+    """The stacks' fused LayerNorm backward (rows arrive through per-warp bulk-copy rings): every output against the fp32 graph
+    of utils/model_utils.py:113-130, the dropout mask against merlot_dropout_apply, the bias gradient against the exact column
+    sums of what the kernel wrote; row counts that leave warps without rows, with one row, and with many ring refills."""
+    g = torch.Generator().manual_seed(rows + H)
+    x = (torch.randn(rows, H, generator=g) * 2 + 0.5).bfloat16()
+    gam = torch.randn(H, generator=g)
+    xr, gr, br = x.float().requires_grad_(True), gam.clone().requires_grad_(True), torch.zeros(H, requires_grad=True)
+    y_ref = O.layer_norm(xr, {"l/gamma": gr, "l/beta": br}, "l")
+    dy = torch.randn(rows, H, generator=g).bfloat16()
+    dres = torch.randn(rows, H, generator=g).bfloat16() if with_dres else None
+    y_ref.backward(dy.float())
+    mu = x.float().mean(-1)
+    rs = torch.rsqrt(x.float().var(-1, unbiased=False) + 1e-5)
+    dx = torch.full((rows, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dmask = torch.full((rows, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dg, db, dbias = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    for rep in range(2):  # twice: the accumulators add up, the ring barriers start fresh every launch
+        ops.layernorm_bwd_fused(dy.to(DEV), x.to(DEV), mu.to(DEV), rs.to(DEV), gam.to(DEV), dx, dg, db,
+                                dres=None if dres is None else dres.to(DEV), dmask=dmask, dbias=dbias, dropout=(p, 7, 3))
+    want = xr.grad + (dres.float() if with_dres else 0.0)
+    assert torch.isfinite(dx.float()).all()
+    assert rel(dx, want) < 6e-3
+    assert rel(dg, 2 * gr.grad) < 2e-3 and rel(db, 2 * br.grad) < 2e-3
+    if p > 0:
+        ref_mask = torch.empty_like(dx)
+        ops.dropout_apply(dx, ref_mask, p, 7, 3)
+        assert torch.equal(dmask, ref_mask)
+        assert rel(dbias, 2 * dmask.float().sum(0)) < 1e-5
+        kept = float((dmask != 0).float().mean())
+        assert abs(kept - (1 - p)) < (0.2 if rows * H < 4096 else 0.02)
+    else:
+        assert rel(dbias, 2 * dx.float().sum(0)) < 1e-5
+
+
 def test_softmax_ce_and_l2norm(ops):
     g = torch.Generator().manual_seed(0)
     R, Cn, ld = 37, 50370, 50432
