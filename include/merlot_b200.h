@@ -360,6 +360,18 @@ int merlot_avgpool2_same_bwd(const void* dy_bf16, int N, int h, int w, int C, vo
 int merlot_col2im3x3(const void* dcol_bf16, int N, int h, int w, int C, int stride, int ld, void* dx_bf16, void* stream);
 /* weight-standardisation backward: dw[rows, cout] += d(standardise)/dw applied to dws[rows(, ld), cout] */
 int merlot_ws_weights_bwd(const float* dws, int ld_dws, const float* w, int rows, int cout, float* dw, void* stream);
+/* The same two operators for EVERY conv kernel of the stem in one launch each (the standardised operands depend on the
+ * parameters only; the gradients meet at the end of the stem's backward pass).  items_dev: device array; item i serves blocks
+ * [block0_i, block0_{i+1}) with block0_0 = 0 and 32 output channels per block, n_blocks = sum ceil(cout_i / 32). */
+typedef struct {
+  const float* w;    /* fp32 [rows, cout] kernel (flattened HWIO) */
+  void* out;         /* bf16 [rows_pad, cout] standardised operand (forward) */
+  const float* dws;  /* fp32 [rows(, ld_dws), cout] gradient of the standardised operand (backward) */
+  float* dw;         /* fp32 [rows, cout] accumulated kernel gradient (backward) */
+  int rows, rows_pad, cout, ld_dws, block0, reserved;
+} merlot_ws_item_t;
+int merlot_ws_weights_multi(const merlot_ws_item_t* items_dev, int n_items, int n_blocks, void* stream);
+int merlot_ws_weights_bwd_multi(const merlot_ws_item_t* items_dev, int n_items, int n_blocks, void* stream);
 int merlot_add_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 
 /* bench.py roofline support: time every K1 launch with CUDA events on its own stream between begin/end.

@@ -183,6 +183,12 @@ class MaskDesc(C.Structure):
     ]
 
 
+class WsItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("dws", C.c_void_p), ("dw", C.c_void_p),
+                ("rows", C.c_int), ("rows_pad", C.c_int), ("cout", C.c_int), ("ld_dws", C.c_int), ("block0", C.c_int),
+                ("reserved", C.c_int)]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [
         ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("p_bf16", C.c_void_p),

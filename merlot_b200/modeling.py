@@ -396,12 +396,15 @@ class MerlotModel(object):
             site[0] += 1
             return bf.get(f"stem.{tag}.{site[0]}" if save else f"stem.{tag}", (rows, cols), torch.bfloat16)
 
+        plan = self._ws_plan()
+        plan.standardise()  # :56-60 (fp32 moments, bf16 operand) for every conv kernel of the stem in one launch
+
         def conv(x, h, w, cin, kname, k, tag, stride=1, sub_half=False):
             wk = st.P(kname)  # fp32 [k*k*cin, cout]
             rows, cout = wk.shape
             assert rows == k * k * cin, (kname, rows, k, cin)
             kp = (rows + 7) // 8 * 8
-            wstd = ops.ws_weights(wk, kp)  # :56-60 (fp32 moments, bf16 operand)
+            wstd = plan.wstd[kname]
             if k == 1:
                 a, ho, wo = x, h, w
             else:
@@ -460,6 +463,17 @@ class MerlotModel(object):
         self._stem_tape = tape if save else None
         return x, h, w
 
+    def _ws_plan(self):
+        """The stem's conv kernels as one table (ops.WsPlan), cached on the store (the arenas' addresses never change)."""
+        st = self.store
+        names = [n for n in st.entries if "resnet50lite" in n and n.endswith("/kernel")]
+        key = tuple(st.P(n).data_ptr() for n in names)
+        plan = getattr(st, "_ws_plan_cache", None)
+        if plan is None or plan.key != key:
+            plan = ops.WsPlan({n: st.P(n) for n in names}, {n: st.G(n) for n in names}, st.device)
+            st._ws_plan_cache = plan
+        return plan
+
     def _hybrid_stem_backward(self, d_out, N):
         """Gradient of _hybrid_stem: walks the tape backwards.  d_out: bf16 gradient of the stem output.  Parameter gradients are
         ACCUMULATED into the arena (conv kernels through the weight-standardisation backward, GroupNorm gamma/beta directly);
@@ -470,6 +484,8 @@ class MerlotModel(object):
         grads = {tape[-1][1]["y"].data_ptr(): d_out}
         red = bf.get("stem.gn_red", (N * 64,), torch.float32)
         ctr = [0]
+        plan = self._ws_plan()  # holds the forward's standardised operands; the wgrad GEMMs accumulate into its gradient arena
+        plan.zero_grads()
 
         def D(rows, cols):
             ctr[0] += 1
@@ -510,14 +526,13 @@ class MerlotModel(object):
                 else:
                     a = bf.get("stem.col", (M, kp), torch.bfloat16)
                     ops.im2col3x3(r["x"], N, r["h"], r["w"], r["cin"], r["stride"], a, sub_half=r["sub_half"])
-                dws = bf.get("stem.dws", (kp, cout), torch.float32, zero=True)
+                dws = plan.dws[r["kname"]]
                 ops.gemm(a, dy, a_mn_major=True, b_mn_major=True, out=dws, atomic=True, M=kp, N=cout, K=M)  # d(standardised kernel)
-                ops.ws_weights_bwd(dws, wk, st.G(r["kname"]))
                 if r["sub_half"]:
                     if trace is not None:
                         trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=None))
                     continue  # the image itself needs no gradient
-                wstd = ops.ws_weights(wk, kp)
+                wstd = plan.wstd[r["kname"]]
                 if r["k"] == 1:
                     dx = D(M, kp)
                     ops.gemm(dy, wstd, out=dx)  # dx[M, cin] = dy[M, cout] . wstd[cin, cout]^T
@@ -529,6 +544,7 @@ class MerlotModel(object):
                 if trace is not None:
                     trace.append(dict(kind=kind, r=r, dy=dy.clone(), dx=dx.clone()))
                 acc(r["x"], dx)
+        plan.backward()  # weight-standardisation backward of every conv kernel: arena gradients += d(standardise)/dw . dws
 
     def _side_stream(self):
         """Stream for the language-only stack (set MERLOT_NO_SIDE_STREAM=1 to serialise everything on one stream)."""

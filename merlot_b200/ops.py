@@ -370,6 +370,47 @@ def ws_weights_bwd(dws, w2d, dw2d):
                                           C.c_void_p(dw2d.data_ptr()), _stream()))
 
 
+class WsPlan:
+    """Every conv kernel of the hybrid stem as one table for merlot_ws_weights_multi / merlot_ws_weights_bwd_multi:
+    `wstd[name]` bf16 [rows_pad, cout] standardised operands, `dws[name]` fp32 [rows_pad, cout] views of ONE gradient arena
+    (zeroed with a single memset before the wgrad GEMMs accumulate into it)."""
+
+    def __init__(self, kernels, grads, device):
+        # kernels / grads: {name: fp32 [rows, cout] parameter / gradient views of the arenas}, in creation order
+        self.names = list(kernels)
+        total, offs = 0, {}
+        for n in self.names:
+            rows, cout = kernels[n].shape
+            kp = (rows + 7) // 8 * 8
+            offs[n] = (total, kp, cout)
+            total += kp * cout
+        self.dws_arena = torch.zeros(total, dtype=torch.float32, device=device)
+        self.wstd_arena = torch.empty(total, dtype=torch.bfloat16, device=device)
+        self.wstd = {n: self.wstd_arena[o:o + kp * c].view(kp, c) for n, (o, kp, c) in offs.items()}
+        self.dws = {n: self.dws_arena[o:o + kp * c].view(kp, c) for n, (o, kp, c) in offs.items()}
+        items = (L.WsItem * len(self.names))()
+        b0 = 0
+        for i, n in enumerate(self.names):
+            rows, cout = kernels[n].shape
+            it = items[i]
+            it.w, it.out, it.dws, it.dw = kernels[n].data_ptr(), self.wstd[n].data_ptr(), self.dws[n].data_ptr(), grads[n].data_ptr()
+            it.rows, it.rows_pad, it.cout, it.ld_dws, it.block0 = rows, offs[n][1], cout, cout, b0
+            b0 += (cout + 31) // 32
+        self.n_blocks = b0
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
+        self.items_dev = raw.to(device)
+        self.key = tuple(kernels[n].data_ptr() for n in self.names)
+
+    def standardise(self):
+        L.check(L.lib().merlot_ws_weights_multi(C.c_void_p(self.items_dev.data_ptr()), len(self.names), self.n_blocks, _stream()))
+
+    def zero_grads(self):
+        self.dws_arena.zero_()
+
+    def backward(self):
+        L.check(L.lib().merlot_ws_weights_bwd_multi(C.c_void_p(self.items_dev.data_ptr()), len(self.names), self.n_blocks, _stream()))
+
+
 def add_bf16(a, b, out):
     L.check(L.lib().merlot_add_bf16(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
                                     C.c_longlong(a.numel()), _stream()))

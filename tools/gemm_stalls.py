@@ -30,7 +30,7 @@ big = (torch.randn(8192, 8192, generator=g) * 0.1).bfloat16().to(dev)
 obig = torch.empty(8192, 8192, dtype=torch.bfloat16, device=dev)
 
 
-def probe(name, fn):
+def probe(name, fn, k=None):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -47,9 +47,13 @@ def probe(name, fn):
     f = lambda t: f"{t.mean().item():9.0f}"
     print(f"{name:34s} tiles/CTA {tiles.min().item():.0f}-{tiles.max().item():.0f} | total{f(mx[:,0])} cyc/tile{f(mx[:,0]/mx[:,7])}"
           f" | mma: wait_full{f(mx[:,1])} wait_tmem_empty{f(mx[:,2])} | tma: wait_empty{f(mx[:,3])}"
-          f" | epi: wait_tmem_full{f(mx[:,4])} wait_staging{f(mx[:,5])} work{f(mx[:,6])}", flush=True)
+          f" | epi: wait_tmem_full{f(mx[:,4])} wait_staging{f(mx[:,5])} work{f(mx[:,6])}"
+          + (f" | mma-warp busy per MMA {((mx[:,0] - mx[:,1] - mx[:,2]) / (mx[:,7] * (k / 16))).mean().item():6.1f} cyc" if k else ""), flush=True)
 
 
+for bn in (128, 192, 256):  # in-situ cost of one 128 x BN x 16 MMA (isolated floors: 64 / 96 / 128 cycles, tools/micro/mma_bench*.cu)
+    probe(f"QKV plain BN={bn}", lambda: ops.gemm(x, wqkv, b_mn_major=True, out=oqkv, block_n=bn), k=H)
+    probe(f"FFN2 plain (K=3072) BN={bn}", lambda: ops.gemm(xi, w2, b_mn_major=True, out=oh, block_n=bn), k=I)
 probe("QKV plain", lambda: ops.gemm(x, wqkv, b_mn_major=True, out=oqkv))
 probe("QKV +bias", lambda: ops.gemm(x, wqkv, b_mn_major=True, bias=b3, out=oqkv))
 probe("FFN1 plain", lambda: ops.gemm(x, w1, b_mn_major=True, out=oi))
@@ -57,4 +61,4 @@ probe("FFN1 +bias+gelu dual", lambda: ops.gemm(x, w1, b_mn_major=True, bias=b1, 
 probe("FFN2 plain (K=3072)", lambda: ops.gemm(xi, w2, b_mn_major=True, out=oh))
 probe("FFN2-dgrad plain", lambda: ops.gemm(x, w2, out=oi, M=M, N=I, K=H))
 probe("FFN2-dgrad dgelu", lambda: ops.gemm(x, w2, out=oi, dgelu_aux=oi2, M=M, N=I, K=H))
-probe("8192^3 1-CTA BN=256", lambda: ops.gemm(big, big, out=obig, block_n=256))
+probe("8192^3 1-CTA BN=256", lambda: ops.gemm(big, big, out=obig, block_n=256), k=8192)

@@ -139,6 +139,27 @@ def add_bf16(a, b, out):
     out.copy_(a.float() + b.float())
 
 
+class WsPlan:  # ops.WsPlan: all conv kernels standardised up front, their gradients standardised back at the end
+    def __init__(self, kernels, grads, device):
+        self.names, self.k, self.g = list(kernels), kernels, grads
+        self.wstd = {}
+        self.dws = {n: torch.zeros((k.shape[0] + 7) // 8 * 8, k.shape[1]) for n, k in kernels.items()}
+        self.key = tuple(k.data_ptr() for k in kernels.values())
+
+    def standardise(self):
+        for n, k in self.k.items():
+            self.wstd[n] = ws_weights(k, (k.shape[0] + 7) // 8 * 8)
+
+    def zero_grads(self):
+        for d in self.dws.values():
+            d.zero_()
+
+    def backward(self):
+        for n, k in self.k.items():
+            ws_weights_bwd(self.dws[n], k, self.g[n])
+
+
+ops.WsPlan = WsPlan
 for name, fn in dict(ws_weights=ws_weights, im2col3x3=im2col3x3, gemm=gemm, group_norm_fwd=group_norm_fwd, group_norm_bwd=group_norm_bwd,
                      avgpool2_same=avgpool2_same, avgpool2_same_bwd=avgpool2_same_bwd, col2im3x3=col2im3x3, ws_weights_bwd=ws_weights_bwd,
                      add_bf16=add_bf16).items():
@@ -159,6 +180,7 @@ class Bufs:
 
 
 fake = types.SimpleNamespace(store=st, _bufs=Bufs(), _resnet_layers=LAYERS, _save=True)
+fake._ws_plan = lambda: modeling.MerlotModel._ws_plan(fake)
 N = 2
 gen = torch.Generator().manual_seed(1)
 img = torch.rand(N, 64, 96, 3, generator=gen)

@@ -9,6 +9,8 @@ sys.path.insert(0, ".")
 import bench  # noqa: E402
 from merlot_b200.train import model_fn_builder, synthetic_batch  # noqa: E402
 
+if "--hybrid-stem" in sys.argv:  # merlot.yaml as shipped
+    bench.STEM = "hybrid"
 cfg = bench.load_config()
 fn = model_fn_builder(cfg)
 feats = synthetic_batch(cfg, bench.PER_GPU_BATCH, seed=0)
