@@ -17,12 +17,12 @@
 
 namespace mb {
 
-// Weight standardisation, forward and backward.  A block of 8 warps owns 32 neighbouring output channels: lane = channel
+// Weight standardisation, forward and backward.  A block of WS_WARPS warps owns 32 neighbouring output channels: lane = channel
 // (every load is one coalesced 128-byte row segment), the warps split the rows (kh, kw, cin) and meet in shared memory once
 // per moment.  History: one THREAD per channel (64..1024 threads in all, a serial loop over up to 2304 rows: 83 us per launch,
 // 107 launches per step) -> one warp per channel (19 us, but 32 memory wavefronts per load: lanes on different rows) -> this.
 constexpr int WS_CH = 32;    // channels per block
-constexpr int WS_WARPS = 8;  // row lanes
+constexpr int WS_WARPS = 32;  // row lanes (1024 threads: the loops over up to 2304 rows are latency chains, 374 us at 8 warps)
 __device__ __forceinline__ float ws_block_sum(float v, float (*red)[WS_CH], int warp, int lane) {
   __syncthreads();  // the previous use of `red` is over
   red[warp][lane] = v;
@@ -37,6 +37,7 @@ __device__ __forceinline__ void ws_channels(const float* __restrict__ w, int row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = c0 + lane;
   const bool ok = c < cout;
   float mean = 0.f;
+#pragma unroll 8
   for (int r = warp; r < rows; r += WS_WARPS) mean += ok ? w[(size_t)r * cout + c] : 0.f;
   mean = ws_block_sum(mean, red, warp, lane) / (float)rows;
   float var = 0.f;
@@ -396,6 +397,7 @@ __device__ __forceinline__ void ws_bwd_channels(const float* __restrict__ dws, i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = c0 + lane;  // same mapping as ws_channels
   const bool ok = c < cout;
   float mean = 0.f;
+#pragma unroll 8
   for (int r = warp; r < rows; r += WS_WARPS) mean += ok ? w[(size_t)r * cout + c] : 0.f;
   mean = ws_block_sum(mean, red, warp, lane) / (float)rows;
   float var = 0.f;
