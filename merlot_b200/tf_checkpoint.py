@@ -71,12 +71,59 @@ def _crc32c_table() -> List[int]:
 _CRC_TABLE = _crc32c_table()
 
 
-def crc32c(data: bytes, crc: int = 0) -> int:
-    """CRC-32C (Castagnoli), the checksum of leveldb blocks and bundle entries.  crc32c(b"123456789") == 0xE3069283."""
-    c = crc ^ 0xFFFFFFFF
+def _crc32c_scalar(data, c: int) -> int:  # raw register update (no init / final xor)
     for b in data:
         c = _CRC_TABLE[(c ^ b) & 0xFF] ^ (c >> 8)
-    return c ^ 0xFFFFFFFF
+    return c
+
+
+_CRC_LANE = 4096  # bytes per lane of the vectorised path
+_CRC_NP = None    # (byte table as uint32 array, 4 x 256 "advance the register by _CRC_LANE zero bytes" tables)
+
+
+def _crc32c_np_tables():
+    global _CRC_NP
+    if _CRC_NP is None:
+        tab = np.array(_CRC_TABLE, dtype=np.uint32)
+        # the register update is linear over GF(2): advance the 32 basis registers through _CRC_LANE zero bytes ...
+        basis = (np.uint32(1) << np.arange(32, dtype=np.uint32)).astype(np.uint32)
+        for _ in range(_CRC_LANE):
+            basis = tab[basis & np.uint32(0xFF)] ^ (basis >> np.uint32(8))
+        # ... and fold them into one 256-entry table per register byte
+        shift = np.zeros((4, 256), dtype=np.uint32)
+        for byte in range(4):
+            for v in range(256):
+                acc = np.uint32(0)
+                for bit in range(8):
+                    if v >> bit & 1:
+                        acc ^= basis[8 * byte + bit]
+                shift[byte, v] = acc
+        _CRC_NP = (tab, shift)
+    return _CRC_NP
+
+
+def crc32c(data, crc: int = 0) -> int:
+    """CRC-32C (Castagnoli), the checksum of leveldb blocks and bundle entries.  crc32c(b"123456789") == 0xE3069283.
+    Buffers of 64 KiB and more take a vectorised path: the buffer is cut into lanes of 4 KiB whose registers advance together
+    (one table lookup per byte position for ALL lanes), and the lane results are chained with the precomputed linear map
+    "advance a register through 4 KiB of zeros" -- ~150 MB/s in NumPy against ~5 MB/s for the byte loop, which matters for
+    the ~1 GB of variables in a MERLOT checkpoint."""
+    c = crc ^ 0xFFFFFFFF
+    n = len(data)
+    if n < (1 << 16):
+        return _crc32c_scalar(bytes(data), c) ^ 0xFFFFFFFF
+    tab, shift = _crc32c_np_tables()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.reshape(-1).view(np.uint8)
+    lanes = n // _CRC_LANE
+    cols = np.ascontiguousarray(buf[:lanes * _CRC_LANE].reshape(lanes, _CRC_LANE).T)  # [_CRC_LANE, lanes]: one row per byte position
+    reg = np.zeros(lanes, dtype=np.uint32)
+    m = np.uint32(0xFF)
+    e = np.uint32(8)
+    for j in range(_CRC_LANE):
+        reg = tab[(reg ^ cols[j]) & m] ^ (reg >> e)
+    for p in reg.tolist():  # chain: register after lane i = advance(register before) ^ lane-local register
+        c = int(shift[0, c & 0xFF] ^ shift[1, (c >> 8) & 0xFF] ^ shift[2, (c >> 16) & 0xFF] ^ shift[3, c >> 24]) ^ p
+    return _crc32c_scalar(buf[lanes * _CRC_LANE:].tobytes(), c) ^ 0xFFFFFFFF
 
 
 def mask_crc(crc: int) -> int:
@@ -304,7 +351,7 @@ def load_checkpoint(prefix: str, names: Optional[Iterable[str]] = None, verify_c
         sid = int(e["shard_id"])
         if sid not in shards:
             shards[sid] = np.memmap(f"{prefix}.data-{sid:05d}-of-{header['num_shards']:05d}", dtype=np.uint8, mode="r")
-        raw = bytes(shards[sid][int(e["offset"]):int(e["offset"]) + int(e["size"])])
+        raw = shards[sid][int(e["offset"]):int(e["offset"]) + int(e["size"])].tobytes()
         if len(raw) != int(e["size"]):
             raise CheckpointFormatError(f"{name}: data shard is shorter than the index says")
         if verify_checksums and e["crc32c"] is not None and mask_crc(crc32c(raw)) != e["crc32c"]:

@@ -95,6 +95,21 @@ def _write_checkpoint(prefix, tensors, compress=False):
         f.write(bytes(data))
 
 
+def test_crc32c_vectorised_path_matches_the_byte_loop():
+    """Buffers >= 64 KiB take the lane-parallel NumPy path (tensor payloads of a real checkpoint): same register as the byte
+    loop for lengths around the lane and threshold boundaries, with and without a running crc; and RFC 3720's all-zero /
+    all-ones / ascending vectors scaled past the threshold agree with the byte loop too."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n in (65535, 65536, 65537, 4096 * 17 + 5, 300001):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert T.crc32c(d) == T._crc32c_scalar(d, 0xFFFFFFFF) ^ 0xFFFFFFFF
+        assert T.crc32c(d, crc=0x1234ABCD) == T._crc32c_scalar(d, 0x1234ABCD ^ 0xFFFFFFFF) ^ 0xFFFFFFFF
+        assert T.crc32c(np.frombuffer(d, dtype=np.uint8)) == T.crc32c(d)  # memmap slices arrive as arrays
+    for d in (bytes(70000), b"\xff" * 70000, bytes(range(256)) * 300):
+        assert T.crc32c(d) == T._crc32c_scalar(d, 0xFFFFFFFF) ^ 0xFFFFFFFF
+
+
 # ---- known answers for the primitives ---------------------------------------------------------------------------
 def test_primitive_known_answers():
     assert T.crc32c(b"123456789") == 0xE3069283            # the standard CRC-32C check value
