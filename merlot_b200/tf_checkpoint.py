@@ -106,7 +106,7 @@ def crc32c(data, crc: int = 0) -> int:
     """CRC-32C (Castagnoli), the checksum of leveldb blocks and bundle entries.  crc32c(b"123456789") == 0xE3069283.
     Buffers of 64 KiB and more take a vectorised path: the buffer is cut into lanes of 4 KiB whose registers advance together
     (one table lookup per byte position for ALL lanes), and the lane results are chained with the precomputed linear map
-    "advance a register through 4 KiB of zeros" -- ~150 MB/s in NumPy against ~5 MB/s for the byte loop, which matters for
+    "advance a register through 4 KiB of zeros" -- ~65 MB/s in NumPy against ~5 MB/s for the byte loop, which matters for
     the ~1 GB of variables in a MERLOT checkpoint."""
     c = crc ^ 0xFFFFFFFF
     n = len(data)
