@@ -22,6 +22,29 @@ def test_library_exports_every_header_symbol():
     assert lib.merlot_abi_version() == 1
 
 
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The descriptor structs of include/merlot_b200.h compiled by gcc (sizeof and the offset of the last member) against their
+    ctypes mirrors in merlot_b200/_lib.py: a field added on one side only would shift every later argument silently."""
+    import ctypes
+    import subprocess
+    pairs = [("merlot_gemm_t", _lib.GemmDesc), ("merlot_attn_t", _lib.AttnDesc), ("merlot_ln_t", _lib.LnDesc),
+             ("merlot_ln_bwd_t", _lib.LnBwdDesc), ("merlot_layer_params_t", _lib.LayerParams), ("merlot_stack_t", _lib.StackDesc),
+             ("merlot_mask_t", _lib.MaskDesc), ("merlot_adamw_t", _lib.AdamDesc), ("merlot_ws_item_t", _lib.WsItem)]
+    src = tmp_path / "sizes.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "merlot_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        lines.append(f'  printf("{cname} %zu %zu\\n", sizeof({cname}), offsetof({cname}, {last}));')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict((ln.split()[0], tuple(int(v) for v in ln.split()[1:])) for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        last = cls._fields_[-1][0]
+        assert out[cname] == (ctypes.sizeof(cls), getattr(cls, last).offset), (cname, out[cname], ctypes.sizeof(cls), getattr(cls, last).offset)
+
+
 def test_neatconfig_errors_mirror_reference():  # utils/neat_config.py:55-61
     with pytest.raises(ValueError, match="missing model"):
         NeatConfig.from_dict({"data": {}, "optimizer": {}, "device": {"output_dir": "x"}})
