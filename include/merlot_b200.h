@@ -121,6 +121,10 @@ typedef struct merlot_attn {
   float* colsum2;              /* colsum only: queries >= colsum_split accumulate here instead of `colsum` (optional) */
   int colsum_split;
   int colsum_valid_q;          /* colsum only: 1 = padding queries contribute nothing (attention_log, modeling.py:192-193) */
+  /* disable_pairwise_lang_attn (model/modeling.py:160-168): with pair_chunk_len > 0 (needs `valid`) position t < pair_viz_len
+   * is a vision token (segment 0) and position t >= pair_viz_len belongs to language chunk (t - pair_viz_len) / pair_chunk_len;
+   * query and key exchange attention iff they share a segment or either one is a vision token.  0 = every valid pair. */
+  int pair_viz_len, pair_chunk_len;
 } merlot_attn_t;
 
 int merlot_attention_fwd(const merlot_attn_t* a, void* stream);
@@ -250,6 +254,7 @@ typedef struct merlot_stack {
    * starts from dy (final LayerNorm); later calls continue from the gradient left in `scratch` by the previous one, so a
    * caller can start the gradient all-reduce of a layer group while the groups below it are still running. */
   int bwd_lo, bwd_hi;
+  int pair_viz_len, pair_chunk_len;            /* disable_pairwise_lang_attn, see merlot_attn_t (0, 0 = off) */
 } merlot_stack_t;
 
 size_t merlot_stack_activation_bytes(const merlot_stack_t* s);

@@ -112,6 +112,7 @@ class AttnDesc(C.Structure):
         ("colsum", C.c_void_p),
         ("d_bias_qkv", C.c_void_p),
         ("colsum2", C.c_void_p), ("colsum_split", C.c_int), ("colsum_valid_q", C.c_int),
+        ("pair_viz_len", C.c_int), ("pair_chunk_len", C.c_int),
     ]
 
 
@@ -169,6 +170,7 @@ class StackDesc(C.Structure):
         ("dh_in", C.c_void_p),
         ("scratch", C.c_void_p),
         ("bwd_lo", C.c_int), ("bwd_hi", C.c_int),
+        ("pair_viz_len", C.c_int), ("pair_chunk_len", C.c_int),
     ]
 
 

@@ -13,7 +13,7 @@ constexpr int EXQ = 8;  // query rows per CTA
 // grid (ceil(S / EXQ), B); 256 threads, thread t walks keys t, t + 256, ...
 __global__ void __launch_bounds__(256) attn_probs_export_kernel(const bf16* __restrict__ qkv, int ld_qkv, const uint8_t* __restrict__ valid,
                                                                 const float* __restrict__ lse, float* __restrict__ out, int B, int S,
-                                                                int heads, float scale) {
+                                                                int heads, float scale, int pair_P, int pair_chunk) {
   extern __shared__ float sm[];
   const int H = heads * 64;
   float* sq = sm;                 // [EXQ][H]   queries of this CTA (fp32), pre-scaled
@@ -31,9 +31,16 @@ __global__ void __launch_bounds__(256) attn_probs_export_kernel(const bf16* __re
   bool vq[EXQ];
 #pragma unroll
   for (int r = 0; r < EXQ; ++r) vq[r] = (q0 + r < S) && (valid == nullptr || valid[tok0 + q0 + r] != 0);
+  // disable_pairwise_lang_attn (model/modeling.py:160-168): segment of a position = 0 for the pair_P vision tokens, 1 + chunk index
+  // otherwise; a pair attends iff same segment or either is a vision token
+  auto seg_of = [&](int t) { return (pair_chunk > 0 && t >= pair_P) ? 1 + (t - pair_P) / pair_chunk : 0; };
+  int sq_seg[EXQ];
+#pragma unroll
+  for (int r = 0; r < EXQ; ++r) sq_seg[r] = seg_of(q0 + r);
   const float inv_heads = 1.0f / (float)heads;
   for (int k = threadIdx.x; k < S; k += 256) {
     const bool vk = valid == nullptr || valid[tok0 + k] != 0;
+    const int k_seg = seg_of(k);
     float acc[EXQ];
 #pragma unroll
     for (int r = 0; r < EXQ; ++r) acc[r] = 0.f;
@@ -57,7 +64,8 @@ __global__ void __launch_bounds__(256) attn_probs_export_kernel(const bf16* __re
 #pragma unroll
       for (int r = 0; r < EXQ; ++r) {
         // utils/transformer.py:109-112: scores*m - 1e10*(1-m); a padding query row has every score equal => uniform
-        const float s = !vq[r] ? 0.f : (vk ? dot[r] : -1e10f);
+        const bool pair_ok = k_seg == 0 || sq_seg[r] == 0 || k_seg == sq_seg[r];
+        const float s = !vq[r] ? 0.f : ((vk && pair_ok) ? dot[r] : -1e10f);
         acc[r] += __expf(s - sl[r * heads + hh]);
       }
     }
@@ -76,6 +84,8 @@ extern "C" int merlot_attention_probs(const merlot_attn_t* a, float* probs_bss, 
   MB_REQUIRE(a && probs_bss && a->qkv && a->lse, MERLOT_EINVAL, "attention_probs: qkv, lse and the output are required");
   MB_REQUIRE(a->head_dim == 64 && a->B > 0 && a->S > 0 && a->heads > 0 && (a->ld_qkv % 8) == 0, MERLOT_ESHAPE,
              "attention_probs: head size 64, ld_qkv %% 8 == 0");
+  MB_REQUIRE(a->pair_chunk_len >= 0 && a->pair_viz_len >= 0 && (a->pair_chunk_len == 0 || a->valid != nullptr), MERLOT_EINVAL,
+             "attention_probs: pair_chunk_len > 0 (disable_pairwise_lang_attn) needs the token-validity mask");
   const int H = a->heads * 64;
   const size_t smem = (size_t)(EXQ * H + EXQ * a->heads) * sizeof(float);
   MB_REQUIRE(smem <= 200 * 1024, MERLOT_ESHAPE, "attention_probs: hidden size too large");
@@ -87,7 +97,7 @@ extern "C" int merlot_attention_probs(const merlot_attn_t* a, float* probs_bss, 
   dim3 grid(ceil_div(a->S, EXQ), a->B);
   attn_probs_export_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const bf16*>(a->qkv), a->ld_qkv,
                                                         reinterpret_cast<const uint8_t*>(a->valid), a->lse, probs_bss, a->B, a->S,
-                                                        a->heads, a->scale);
+                                                        a->heads, a->scale, a->pair_viz_len, a->pair_chunk_len);
   MB_CHECK_LAUNCH();
   return MERLOT_OK;
 }

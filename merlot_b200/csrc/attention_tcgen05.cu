@@ -37,6 +37,7 @@ struct AttnDev {
   float* colsum2;                // optional: queries >= colsum_split accumulate here instead
   int colsum_split;              // 0 = no split
   int colsum_valid_q;            // 1 = only valid (non-padding) queries contribute (attention_log, modeling.py:192-193)
+  int pair_P, pair_chunk;        // disable_pairwise_lang_attn (model/modeling.py:160-168); pair_chunk == 0: off
   int dbg_mode;                  // timing experiments only (merlot_attention_debug_mode): 1 = no arithmetic, 2 = no MMA2, 4 = no MMA1
   unsigned long long* dbg;       // optional phase counters (merlot_attention_debug_counters): [0,8) forward, [8,16) backward
 };
@@ -84,6 +85,25 @@ constexpr float MASKED_LOG2 = -1e10f * LOG2E;
 __device__ __forceinline__ uint32_t range_word(int k, int S) {
   const int n = S - k;
   return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+}
+
+// bits of the 32-position word starting at x0 whose positions lie in [a, b)
+__device__ __forceinline__ uint32_t span_word(int x0, int a, int b) {
+  const int lo = max(a - x0, 0), hi = min(b - x0, 32);
+  if (hi <= lo) return 0u;
+  const uint32_t below_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+  return below_hi & (0xffffffffu << lo);
+}
+// disable_pairwise_lang_attn (model/modeling.py:160-168): segment 0 = the P vision tokens, segment 1 + c = language chunk c;
+// two positions exchange attention iff they share a segment or either is a vision token.  The relation is symmetric, so one
+// helper serves "keys a query may see" (K2) and "queries a key is seen by" (K3, K4).  pair_lo_of: start of the language chunk
+// of position t, or -1 when t is unrestricted (vision token / feature off); pair_word: the partners of such a position
+// inside the 32-position word starting at x0.
+__device__ __forceinline__ int pair_lo_of(int t, int P, int chunk) {
+  return (chunk > 0 && t >= P) ? P + ((t - P) / chunk) * chunk : -1;
+}
+__device__ __forceinline__ uint32_t pair_word(int x0, int lo, int P, int chunk) {
+  return lo < 0 ? 0xffffffffu : (span_word(x0, 0, P) | span_word(x0, lo, lo + chunk));
 }
 
 template <bool HAS_MASK>
@@ -146,6 +166,7 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
   const bool vq = (HAS_MASK && q_in) ? (p.valid[tok0 + q] != 0) : true;
   // a padding QUERY row softmaxes uniformly over all in-range keys: realised as zero scores with every key "valid"
   const float sc2 = vq ? p.scale * LOG2E : 0.f;
+  const int pair_lo = (HAS_MASK && vq) ? pair_lo_of(q, p.pair_P, p.pair_chunk) : -1;  // a padding query row stays uniform over ALL keys
   float m_used = -INFINITY, l_run = 0.f;
 
   constexpr uint32_t idesc_o = make_idesc_bf16(AT_M, AT_D, 0, 1);  // B = V tile, MN-major (rows are keys)
@@ -192,7 +213,8 @@ __global__ void __launch_bounds__(128, 3) attn_fwd_kernel(const __grid_constant_
         tmem_ld_32x32(tS + lane_off + c * 32, r);  // (columns past N = 16 nu hold stale scores: masked to -inf below)
         tmem_wait_ld();
         const uint32_t iw = range_word(k0 + c * 32, S);
-        const uint32_t vw = (HAS_MASK && vq) ? s_mask[(k0 >> 5) + c] : 0xffffffffu;
+        uint32_t vw = (HAS_MASK && vq) ? s_mask[(k0 >> 5) + c] : 0xffffffffu;
+        if (HAS_MASK && pair_lo >= 0) vw &= pair_word(k0 + c * 32, pair_lo, p.pair_P, p.pair_chunk);
         if (iw == 0xffffffffu && vw == 0xffffffffu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -544,6 +566,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
       const int kk = k0 + row_t;  // this thread's key row
       const bool k_in = kk < S;
       const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
+      const int pair_lo = HAS_MASK ? pair_lo_of(kk, p.pair_P, p.pair_chunk) : -1;  // queries this key is seen by
       // a warp whose 32 keys are all out of range contributes exact zeros: written once per item (both buffers: every MMA of
       // the previous item has completed -- its last drain waited for that), arithmetic skipped afterwards
       const bool warp_dead = (k0 + quad * 32) >= S || (p.dbg_mode & 1);
@@ -628,7 +651,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
             const int qb = q0 + u * 16;
             const uint32_t iw = k_in ? ((range_word(qb & ~31, S) >> (qb & 31)) & 0xffffu) : 0u;   // query in range (and this key in range)
             const uint32_t qw = HAS_MASK ? ((s_mask[qb >> 5] >> (qb & 31)) & 0xffffu) : 0xffffu;   // query validity
-            const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk;
+            const uint32_t aw = (HAS_MASK && pair_lo >= 0) ? ((pair_word(qb & ~31, pair_lo, p.pair_P, p.pair_chunk) >> (qb & 31)) & 0xffffu) : 0xffffu;
+            const bool fast = (iw == 0xffffu) && (qw == 0xffffu) && vk && (aw == 0xffffu);
             uint32_t pk[8], dk[8];
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
@@ -643,7 +667,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant
                   pr = ex2_approx(fmaf(__uint_as_float(rs[e + t4]), sc2, ls[t4]));
                 } else {
                   float t = __uint_as_float(rs[e + t4]) * sc2;
-                  t = vk ? t : MASKED_LOG2;
+                  t = (vk && ((aw >> (e + t4)) & 1u)) ? t : MASKED_LOG2;
                   t = ((qw >> (e + t4)) & 1u) ? t : 0.f;  // padding query: uniform row (zero scores)
                   pr = ex2_approx(t + ls[t4]);
                   pr = ((iw >> (e + t4)) & 1u) ? pr : 0.f;
@@ -882,6 +906,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
   const int kk = k0 + tid;
   const bool k_in = kk < S;
   const bool vk = k_in ? (HAS_MASK ? p.valid[tok0 + kk] != 0 : true) : false;
+  const int pair_lo = HAS_MASK ? pair_lo_of(kk, p.pair_P, p.pair_chunk) : -1;  // queries this key is seen by
   const bool warp_live = (k0 + warp * 32) < S;
   const float sc2 = p.scale * LOG2E;
   float acc = 0.f, acc2 = 0.f;
@@ -906,8 +931,9 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
         const uint32_t qw = HAS_MASK ? s_mask[(q0 >> 5) + c] : 0xffffffffu;      // query validity
         const uint32_t sw = range_word(q0 + c * 32, split);                     // query < split -> colsum, else colsum2
         const uint32_t keep = iw & ((HAS_MASK && p.colsum_valid_q) ? qw : 0xffffffffu);  // queries that contribute at all
+        const uint32_t aw = (HAS_MASK && pair_lo >= 0) ? pair_word(q0 + c * 32, pair_lo, p.pair_P, p.pair_chunk) : 0xffffffffu;
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-        if (keep == 0xffffffffu && qw == 0xffffffffu && vk && (sw == 0xffffffffu || sw == 0u)) {
+        if (keep == 0xffffffffu && qw == 0xffffffffu && vk && aw == 0xffffffffu && (sw == 0xffffffffu || sw == 0u)) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             a0 += ex2_approx(fmaf(__uint_as_float(r[e]), sc2, nl[c * 32 + e]));
@@ -918,7 +944,7 @@ __global__ void __launch_bounds__(128, 2) attn_colsum_kernel(const __grid_consta
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             float x = __uint_as_float(r[e]) * sc2;
-            x = vk ? x : MASKED_LOG2;
+            x = (vk && ((aw >> e) & 1u)) ? x : MASKED_LOG2;
             x = ((qw >> e) & 1u) ? x : 0.f;  // padding query: uniform row (zero scores)
             float pr = ex2_approx(x + nl[c * 32 + e]);
             pr = ((keep >> e) & 1u) ? pr : 0.f;
@@ -948,6 +974,8 @@ static int check_common(const merlot_attn_t* a) {
   MB_REQUIRE(a->head_dim == 64, MERLOT_ESHAPE, "attention: head size must be 64 (got %d)", a->head_dim);
   MB_REQUIRE(a->qkv != nullptr && a->ld_qkv >= 3 * a->heads * 64 && (a->ld_qkv % 8) == 0, MERLOT_ESHAPE,
              "attention: qkv must be [tokens, >=3H] with ld %% 8 == 0");
+  MB_REQUIRE(a->pair_chunk_len >= 0 && a->pair_viz_len >= 0 && (a->pair_chunk_len == 0 || a->valid != nullptr), MERLOT_EINVAL,
+             "attention: pair_chunk_len > 0 (disable_pairwise_lang_attn) needs the token-validity mask and non-negative lengths");
   return MERLOT_OK;
 }
 
@@ -965,6 +993,7 @@ static void fill_dev(const merlot_attn_t* a, AttnDev* p) {
   p->colsum2 = a->colsum2;
   p->colsum_split = a->colsum_split;
   p->colsum_valid_q = a->colsum_valid_q;
+  p->pair_P = a->pair_viz_len; p->pair_chunk = a->pair_chunk_len;
   p->dbg = g_attn_dbg;
   p->dbg_mode = g_attn_dbg_mode;
 }

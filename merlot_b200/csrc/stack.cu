@@ -176,6 +176,7 @@ extern "C" int merlot_stack_forward(const merlot_stack_t* s, void* stream_) {
       merlot_attn_t a;
       memset(&a, 0, sizeof(a));
       a.B = s->B; a.S = s->S; a.heads = s->heads; a.head_dim = 64; a.qkv = A.qkv; a.ld_qkv = 3 * H; a.valid = s->valid;
+      a.pair_viz_len = s->pair_viz_len; a.pair_chunk_len = s->pair_chunk_len;
       a.scale = 0.125f; a.ctx = A.ctx; a.ld_ctx = H; a.lse = A.lse;
       RC(merlot_attention_fwd(&a, st));
       if (s->attn_colsum) {
@@ -320,6 +321,7 @@ extern "C" int merlot_stack_backward(const merlot_stack_t* s, void* stream_) {
       merlot_attn_t a;
       memset(&a, 0, sizeof(a));
       a.B = s->B; a.S = s->S; a.heads = s->heads; a.head_dim = 64; a.qkv = A.qkv; a.ld_qkv = 3 * H; a.valid = s->valid;
+      a.pair_viz_len = s->pair_viz_len; a.pair_chunk_len = s->pair_chunk_len;
       a.scale = 0.125f; a.ctx = A.ctx; a.ld_ctx = H; a.lse = A.lse; a.d_ctx = dtmp; a.dsum = dsum; a.dq_accum = dq_acc;
       a.ld_dq = H; a.dqkv = dqkv; a.ld_dqkv = 3 * H; a.d_bias_qkv = P.g_b_qkv;  // bias gradient fused into the finish pass
       RC(merlot_attention_bwd(&a, st));

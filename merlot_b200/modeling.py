@@ -86,7 +86,7 @@ class _Stack:
     """One transformer stack invocation (utils/transformer.py:171-247) through merlot_stack_forward/backward."""
 
     def __init__(self, store, bufs, tag, scope, layers, B, S, valid, h_in, cfg, dropout_p, seed, site, save, colsum=None,
-                 colsum2=None, colsum_split=0, colsum_valid_q=0, probs=None):
+                 colsum2=None, colsum_split=0, colsum_valid_q=0, probs=None, pair=(0, 0)):
         H, I, heads = cfg["hidden_size"], cfg["intermediate_size"], cfg["num_attention_heads"]
         if H % heads != 0 or H // heads != 64:
             raise ValueError("passed in a tensor of shape {} when size_per_head={} and num_attention_heads={}".format(
@@ -112,6 +112,7 @@ class _Stack:
         d.attn_colsum2 = colsum2.data_ptr() if colsum2 is not None else None
         d.attn_colsum_split, d.attn_colsum_valid_q = int(colsum_split), int(colsum_valid_q)
         d.attn_probs = probs.data_ptr() if probs is not None else None
+        d.pair_viz_len, d.pair_chunk_len = int(pair[0]), int(pair[1])  # disable_pairwise_lang_attn (model/modeling.py:160-168)
         self.d, self.bufs, self.tag, self.keep = d, bufs, tag, (valid, h_in, colsum, probs)
 
     def forward(self):
@@ -160,8 +161,6 @@ class MerlotModel(object):
         if cfg.get("num_texts", 1) > 1 and (mask_input or shuffled_idx_img is not None):
             raise NotImplementedError("num_texts > 1 (VCR, model/modeling.py:111-119) is a finetuning/inference path: mask_input and "
                                       "shuffled_idx_img are not combined with it in the reference either (:319-320)")
-        if cfg.get("disable_pairwise_lang_attn", False):
-            raise NotImplementedError("disable_pairwise_lang_attn (model/modeling.py:160-168) not provided yet")
         if not cfg.get("share_params", True):
             raise NotImplementedError("share_params: False (separate langonly_encoder, model/modeling.py:361) not provided yet")
         # hybrid ResNet-lite stem (utils/vision_transformer.py:206-223) instead of the 16x16 patch embedding: forward provided
@@ -348,7 +347,9 @@ class MerlotModel(object):
             probs_j = bf.get("joint.probs", (cfg["num_hidden_layers"], B, Sj, Sj), torch.float32)
         self._joint = _Stack(st, bf, "joint", "encoder", cfg["num_hidden_layers"], B, Sj, valid_j, joint_in, cfg,
                              p_hid if train else 0.0, self._seed, _SITE_JOINT, self._save, colsum=c_viz, colsum2=c_lang,
-                             colsum_split=Pz, colsum_valid_q=1, probs=probs_j)
+                             colsum_split=Pz, colsum_valid_q=1, probs=probs_j,
+                             # :160-168: language chunks attend to the vision tokens and to themselves only
+                             pair=(Pz, self.lang_chunk_length) if cfg.get("disable_pairwise_lang_attn", False) else (0, 0))
         self._y_j = self._joint.forward()
         self._attn_log = None
         if self._log_attention_probs:

@@ -94,7 +94,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     return out
 
 
-def _attn_desc(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[torch.Tensor]) -> L.AttnDesc:
+def _attn_desc(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[torch.Tensor], pair=(0, 0)) -> L.AttnDesc:
     _require_cuda(qkv, valid)
     assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[0] == B * S
     a = L.AttnDesc()
@@ -104,13 +104,14 @@ def _attn_desc(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[to
         assert valid.dtype == torch.uint8 and valid.numel() == B * S and valid.is_contiguous()
         a.valid = valid.data_ptr()
     a.scale = 1.0 / (a.head_dim ** 0.5)
+    a.pair_viz_len, a.pair_chunk_len = int(pair[0]), int(pair[1])  # disable_pairwise_lang_attn (0, 0 = off)
     return a
 
 
 def attention_fwd(qkv: torch.Tensor, B: int, S: int, heads: int, valid: Optional[torch.Tensor] = None,
-                  ctx: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None):
+                  ctx: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None, pair=(0, 0)):
     """K2: ctx[B*S,H] = softmax(mask(q k^T / sqrt(d))) v, reading q/k/v in place from the fused qkv buffer."""
-    a = _attn_desc(qkv, B, S, heads, valid)
+    a = _attn_desc(qkv, B, S, heads, valid, pair)
     H = heads * a.head_dim
     if ctx is None:
         ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device)
@@ -128,10 +129,10 @@ def attention_bwd_workspace(B: int, S: int, heads: int, device) -> torch.Tensor:
     return torch.zeros((n // H, H), dtype=torch.float32, device=device)
 
 
-def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_accum=None, dsum=None):
+def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_accum=None, dsum=None, pair=(0, 0)):
     """K3: dqkv[B*S,3H] from d_ctx.  dq_accum: fp32 workspace of merlot_attention_bwd_workspace_bytes (see the header);
     in atomic mode (long sequences) it must be zero on entry and is returned zeroed."""
-    a = _attn_desc(qkv, B, S, heads, valid)
+    a = _attn_desc(qkv, B, S, heads, valid, pair)
     H = heads * a.head_dim
     dev = qkv.device
     if dqkv is None:
@@ -151,9 +152,9 @@ def attention_bwd(qkv, ctx, d_ctx, lse, B, S, heads, valid=None, dqkv=None, dq_a
     return dqkv
 
 
-def attention_probs(qkv, lse, B, S, heads, valid=None, out=None):
+def attention_probs(qkv, lse, B, S, heads, valid=None, out=None, pair=(0, 0)):
     """Export path: head-mean probabilities [B,S,S] fp32 of one layer (one layer of `self_attn_probs`)."""
-    a = _attn_desc(qkv, B, S, heads, valid)
+    a = _attn_desc(qkv, B, S, heads, valid, pair)
     if out is None:
         out = torch.empty((B, S, S), dtype=torch.float32, device=qkv.device)
     a.lse = lse.data_ptr()
@@ -161,9 +162,9 @@ def attention_probs(qkv, lse, B, S, heads, valid=None, out=None):
     return out
 
 
-def attention_colsum(qkv, lse, colsum, B, S, heads, valid=None):
+def attention_colsum(qkv, lse, colsum, B, S, heads, valid=None, pair=(0, 0)):
     """K4: colsum[B,S] += mean_h sum_q P[b,h,q,k] (recomputed from q,k,lse)."""
-    a = _attn_desc(qkv, B, S, heads, valid)
+    a = _attn_desc(qkv, B, S, heads, valid, pair)
     assert colsum.dtype == torch.float32 and colsum.numel() == B * S
     a.lse, a.colsum = lse.data_ptr(), colsum.data_ptr()
     L.check(L.lib().merlot_attention_colsum(C.byref(a), _stream()))

@@ -414,8 +414,6 @@ class MerlotOracle:
         if cfg.get("num_imgs", 1) != 1:
             raise NotImplementedError("oracle: num_imgs > 1 (modeling.py:111-122) not restated (no shipped config sets it)")
         self.num_texts = cfg.get("num_texts", 1)
-        if cfg.get("disable_pairwise_lang_attn", False):
-            raise NotImplementedError("oracle: disable_pairwise_lang_attn (modeling.py:160-168) not restated")
         if input_ids.dim() == 2:  # :72-77
             self.num_chunks = 1
             self.num_chunks_in_group = 1
@@ -463,7 +461,14 @@ class MerlotOracle:
 
         enc_in = torch.cat([x["x"] for x in pieces], 1)  # :151
         is_valid = torch.cat([x["is_valid"] for x in pieces], 1)  # :152
-        attn_mask = (is_valid[:, None] & is_valid[:, :, None]).to(dt)  # :158,170
+        attn_mask = is_valid[:, None] & is_valid[:, :, None]  # :158
+        if cfg.get("disable_pairwise_lang_attn", False):  # :160-168: segment 0 = vision tokens, 1 + c = language chunk c
+            segment_idx = torch.cat([torch.zeros(self.P, dtype=torch.int64),
+                                     1 + torch.div(torch.arange(self.L), self.lang_chunk_length, rounding_mode="floor")])
+            can_attend = segment_idx[:, None] == segment_idx[None]
+            can_attend = can_attend | (segment_idx == 0)[None] | (segment_idx == 0)[:, None]
+            attn_mask = attn_mask & can_attend[None]
+        attn_mask = attn_mask.to(dt)  # :170
         self.encoder_info = transformer(enc_in, attn_mask, params, "encoder", cfg["num_hidden_layers"],
                                         cfg["num_attention_heads"], return_attn_probs=log_attention_probs)  # :171-174
         self.encoder_hidden_states = {}

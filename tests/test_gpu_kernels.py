@@ -191,6 +191,52 @@ def test_attention_fwd_bwd_colsum(ops, B, S, heads, masked):
     assert rel(colsum, probs.detach().mean(1).sum(1)) < 2e-3  # head-mean, summed over queries (transformer.py:208-209)
 
 
+@pytest.mark.parametrize("B,P,chunk,nch,heads", [(2, 13, 8, 4, 2), (2, 100, 32, 5, 4), (1, 266, 32, 4, 12), (2, 0, 16, 6, 1), (1, 70, 33, 3, 2)])
+def test_attention_disable_pairwise_lang_attn(ops, B, P, chunk, nch, heads):
+    """model/modeling.py:160-168: segment 0 = P vision tokens, segment 1 + c = language chunk c; a pair attends iff it shares a
+    segment or either side is a vision token.  K2 / K3 / K4 and the export kernel take (P, chunk) and derive the partner set of
+    every row arithmetically; the oracle gets the explicit [B, S, S] mask the reference builds.  Chunk boundaries fall inside
+    32-position words, inside and across the 64 / 128-wide tiles, and some tokens are padding."""
+    S = P + chunk * nch
+    g = torch.Generator().manual_seed(S + chunk)
+    H = heads * 64
+    qkv = torch.randn(B * S, 3 * H, generator=g).bfloat16()
+    v2 = torch.ones(B, S, dtype=torch.bool)
+    for b in range(B):  # ragged captions: the tail of some chunks is padding (ids == 0)
+        for c in range(nch):
+            n_pad = int(torch.randint(0, chunk // 2 + 1, (1,), generator=g))
+            if n_pad:
+                v2[b, P + (c + 1) * chunk - n_pad:P + (c + 1) * chunk] = False
+    seg = torch.cat([torch.zeros(P, dtype=torch.int64), 1 + torch.arange(chunk * nch) // chunk])
+    can = (seg[:, None] == seg[None]) | (seg == 0)[None] | (seg == 0)[:, None]
+    mask = (v2[:, None, :] & v2[:, :, None] & can[None]).float()
+    valid = v2.to(torch.uint8).reshape(-1).contiguous().to(DEV)
+    x = qkv.float().reshape(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = (x[i].clone().requires_grad_(True) for i in range(3))
+    probs, ctx4 = O.attention_core(q, k, v, mask)
+    ctx_ref = ctx4.permute(0, 2, 1, 3).reshape(B * S, H)
+    pair = (P, chunk)
+    ctx, lse = ops.attention_fwd(qkv.to(DEV), B, S, heads, valid, pair=pair)
+    assert rel(ctx, ctx_ref) < 1e-2
+    # the mask did something: without it the same inputs give a different context
+    ctx_nopair, _ = ops.attention_fwd(qkv.to(DEV), B, S, heads, valid)
+    assert nch < 2 or rel(ctx_nopair, ctx_ref) > 1e-2
+    d_ctx = (torch.randn(B * S, H, generator=g) * 0.1).bfloat16()
+    dqkv = ops.attention_bwd(qkv.to(DEV), ctx, d_ctx.to(DEV), lse, B, S, heads, valid, pair=pair)
+    ctx_ref.backward(d_ctx.float())
+    ref = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+    for i in range(3):
+        assert rel(dqkv[:, i * H:(i + 1) * H], ref[:, i * H:(i + 1) * H]) < 1.5e-2
+    colsum = torch.zeros(B, S, device=DEV)
+    ops.attention_colsum(qkv.to(DEV), lse, colsum, B, S, heads, valid, pair=pair)
+    assert rel(colsum, probs.detach().mean(1).sum(1)) < 2e-3
+    pm = ops.attention_probs(qkv.to(DEV), lse, B, S, heads, valid, pair=pair)
+    assert rel(pm, probs.detach().mean(1)) < 2e-3
+    # a language token of chunk 0 puts (numerically) nothing on a language token of chunk 1
+    if nch >= 2:
+        assert float(pm[0, P, P + chunk].abs()) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # K5 LayerNorm, CE, l2norm
 # ---------------------------------------------------------------------------------------------------------------

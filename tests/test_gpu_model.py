@@ -99,6 +99,45 @@ def test_pretrain_step_parity(tiny_cfg):
     assert float(store.g.abs().max()) == 0.0 and store.global_step == 1
 
 
+def test_disable_pairwise_lang_attn(tiny_cfg):
+    """model/modeling.py:160-168 through the whole model: with the switch on, the language chunks of the joint encoder see the
+    vision tokens and themselves only -- hidden states, attention_log, the three losses and every gradient against the oracle
+    (which builds the reference's explicit mask), and the result differs from the unrestricted model."""
+    from merlot_b200.modeling import MerlotModel
+    cfg = dict(tiny_cfg, disable_pairwise_lang_attn=True, num_chunks_in_group=4)
+    batch, nc, Lc = 2, 4, 16
+    image, ids, shuf, vid = synth(cfg, batch, nc, Lc, 64, 96, 3)
+    params, store, _ = build(cfg)
+    B, Lj = batch * nc // cfg["num_chunks_in_group"], Lc * cfg["num_chunks_in_group"]
+    draws = O.make_mask_draws(B, Lj, int(Lj * 0.2), cfg["vocab_size"], seed=7)
+    m = MerlotModel(cfg, is_training=False, use_tpu=False, image=image.to(DEV), input_ids=ids.to(DEV), mask_input=True,
+                    shuffled_idx_img=shuf.to(DEV), params=store, mask_draws=draws, save_for_backward=True)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    gm = {"masked_ids": m.lang_mask_info["masked_ids"].cpu().reshape(B, Lj), "masked_idx": m.lang_mask_info["masked_idx"].cpu()}
+    om = O.MerlotOracle(cfg, leaf, image, ids, mask_input=True, shuffled_idx_img=shuf, mask_override=gm)
+    for name in ("viz", "lang"):
+        assert rel(m.encoder_hidden_states[name], om.encoder_hidden_states[name]) < 1e-2
+    for k, v in om.attention_log.items():
+        assert abs(float(m.attention_log[k]) - float(v)) < 2e-3, k
+    free = O.MerlotOracle(dict(cfg, disable_pairwise_lang_attn=False), params, image, ids, mask_input=True, shuffled_idx_img=shuf,
+                          mask_override=gm)
+    assert rel(free.encoder_hidden_states["lang"], om.encoder_hidden_states["lang"]) > 3e-3  # the switch changes the function (near-uniform attention at this init: ~1e-2)
+    ll, _ = m.mask_loss()
+    cl, _ = m.contrastive_loss()
+    tl, _ = m.temporal_loss(shuf.to(DEV), vid.to(DEV))
+    total_ref, _ = O.pretrain_losses(om, shuf, vid)
+    total = float(ll) + float(cl) + float(tl)
+    assert abs(total - float(total_ref)) <= 1e-3 * abs(float(total_ref))
+    store.g.zero_()
+    m.backward()
+    total_ref.backward()
+    grads = store.to_tf_dict("g")
+    for k, v in leaf.items():
+        if v.grad is None or float(v.grad.norm()) < 1e-7:
+            continue
+        assert rel(grads[k], v.grad) < 4e-2, k
+
+
 def test_forward_only_2d_ids_config1(tiny_cfg):
     """BASELINE config 1 shape family: 2-D input_ids => num_chunks = 1 (model/modeling.py:72-77), no masking, no losses."""
     from merlot_b200.modeling import MerlotModel
