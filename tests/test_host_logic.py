@@ -45,6 +45,26 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         assert out[cname] == (ctypes.sizeof(cls), getattr(cls, last).offset), (cname, out[cname], ctypes.sizeof(cls), getattr(cls, last).offset)
 
 
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): ONE JSON line on stdout with the contract's keys,
+    the oracle port named as such, zero device traffic and no GPU launches."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "segments/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert "workload" in d["config"]
+
+
 def test_neatconfig_errors_mirror_reference():  # utils/neat_config.py:55-61
     with pytest.raises(ValueError, match="missing model"):
         NeatConfig.from_dict({"data": {}, "optimizer": {}, "device": {"output_dir": "x"}})
