@@ -65,6 +65,40 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"]
 
 
+def test_pairwise_partner_words_equal_the_reference_mask():
+    """disable_pairwise_lang_attn (model/modeling.py:160-168): the attention kernels never see an [S, S] mask -- every row
+    derives its partners as two bit ranges per 32-position word (csrc/attention_tcgen05.cu: span_word / pair_lo_of / pair_word).
+    The same integer arithmetic restated here must reproduce the reference's segment_idx construction bit for bit, for chunk
+    lengths that are not word-aligned, P = 0, single-token chunks, and the 16-bit extraction K3 uses."""
+    def span_word(x0, a, b):
+        lo, hi = max(a - x0, 0), min(b - x0, 32)
+        if hi <= lo:
+            return 0
+        return (0xFFFFFFFF if hi >= 32 else (1 << hi) - 1) & ((0xFFFFFFFF << lo) & 0xFFFFFFFF)
+
+    def pair_lo_of(t, P, chunk):
+        return P + ((t - P) // chunk) * chunk if (chunk > 0 and t >= P) else -1
+
+    def pair_word(x0, lo, P, chunk):
+        return 0xFFFFFFFF if lo < 0 else (span_word(x0, 0, P) | span_word(x0, lo, lo + chunk))
+
+    for P, chunk, nch in [(13, 8, 4), (100, 32, 5), (0, 16, 6), (70, 33, 3), (31, 1, 40), (64, 64, 2)]:
+        S = P + chunk * nch
+        seg = torch.cat([torch.zeros(P, dtype=torch.int64), 1 + torch.arange(chunk * nch) // chunk])  # :162-164
+        can = (seg[:, None] == seg[None]) | (seg == 0)[None] | (seg == 0)[:, None]                    # :165-167
+        for t in range(S):
+            lo = pair_lo_of(t, P, chunk)
+            bits = []
+            for x0 in range(0, (S + 31) // 32 * 32, 32):
+                w = pair_word(x0, lo, P, chunk)
+                bits += [(w >> i) & 1 for i in range(32)]
+            assert bits[:S] == can[t].int().tolist(), (P, chunk, t)
+            for qb in range(0, S, 16):  # K3: 16 queries at a time out of the 32-position word
+                aw = (pair_word(qb & ~31, lo, P, chunk) >> (qb & 31)) & 0xFFFF
+                n = min(16, S - qb)
+                assert [(aw >> i) & 1 for i in range(n)] == can[t, qb:qb + n].int().tolist()
+
+
 def test_neatconfig_errors_mirror_reference():  # utils/neat_config.py:55-61
     with pytest.raises(ValueError, match="missing model"):
         NeatConfig.from_dict({"data": {}, "optimizer": {}, "device": {"output_dir": "x"}})
